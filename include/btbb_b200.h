@@ -1,0 +1,184 @@
+/*
+ * btbb_b200.h -- C ABI of the B200-native Bluetooth BR/EDR packet-detection path.
+ *
+ * This is the drop-in boundary: plain C, pointers and
+ * sizes only.  Every entry point names the reference interface it replaces
+ * (paths relative to the libbtbb tree, lib/src/).  The classic btbb_* surface
+ * of btbb.h (btbb_init / btbb_find_ac / btbb_packet_* / btbb_decode*) is
+ * exported by the same shared object (see include/btbb.h); it is implemented
+ * on top of the batch entry points declared here.
+ *
+ * There is NO CPU fallback behind any of these calls: they launch sm_100a
+ * kernels and return a negative BTBB_B200_E* code when CUDA is unavailable.
+ */
+#ifndef BTBB_B200_H
+#define BTBB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTBB_B200_LAP_ANY 0xffffffffu   /* btbb.h:95 LAP_ANY */
+
+/* error codes (all negative; the reference uses -1 for every failure, btbb.h:69-73) */
+#define BTBB_B200_OK            0
+#define BTBB_B200_EINVAL       -1   /* bad argument (e.g. max_ac_errors outside 0..5, bluetooth_packet.c:282) */
+#define BTBB_B200_ECUDA        -2   /* CUDA runtime / driver error, no device, wrong arch */
+#define BTBB_B200_ENOMEM       -3
+#define BTBB_B200_EOVERFLOW    -4   /* more hits than the caller's buffer holds (count is still returned) */
+
+/* One detected access code.  16 bytes, SURVEY.md 8d "16 B written per hit". */
+typedef struct btbb_b200_hit {
+	int64_t  offset;      /* symbol index of the first sync-word symbol   (btbb_find_ac return value) */
+	uint32_t lap;         /* recovered / requested LAP                     (init_packet, bluetooth_packet.c:201) */
+	uint8_t  ac_errors;   /* corrected bit errors in the access code       (btbb_packet_get_ac_errors) */
+	uint8_t  pad[3];      /* zero */
+} btbb_b200_hit;
+
+/* Result of the per-packet chain for one packet (btbb_decode_header + btbb_decode_payload,
+ * bluetooth_packet.c:1198-1297), or of try_clock + crc_check (:1178-1195, :708-769). */
+typedef struct btbb_b200_decoded {
+	int32_t  header_ok;             /* btbb_decode_header() return; try_clock mode: unfec13 success */
+	int32_t  rv;                    /* btbb_decode_payload()/crc_check() return: 0,1,2,10,1000 */
+	uint8_t  uap;                   /* pkt->UAP */
+	uint8_t  type;                  /* pkt->packet_type */
+	uint8_t  lt_addr;               /* pkt->packet_lt_addr */
+	uint8_t  flags;                 /* pkt->packet_flags */
+	uint8_t  hec;                   /* pkt->packet_hec */
+	uint8_t  llid;                  /* pkt->payload_llid */
+	uint8_t  flow;                  /* pkt->payload_flow */
+	uint8_t  has_payload;           /* BTBB_HAS_PAYLOAD flag */
+	int32_t  payload_header_length; /* pkt->payload_header_length */
+	int32_t  payload_length;        /* pkt->payload_length (bytes) */
+	uint32_t header_packed;         /* btbb_packet_get_header_packed() */
+	uint8_t  payload[344];          /* btbb_get_payload_packed() when rv >= 2, else zero */
+} btbb_b200_decoded;
+
+/* Per-packet input of the decode chain (what btbb_packet_set_data + set_uap + flags carry). */
+typedef struct btbb_b200_pkt_in {
+	int64_t  offset;     /* symbol index of the sync word's first symbol in the stream */
+	int32_t  length;     /* symbols available from offset (clamped to 3125, bluetooth_packet.c:472) */
+	uint32_t clkn;       /* CLK1-27 as stored in pkt->clkn (i.e. already >>1); only the low 6 bits whiten */
+	uint8_t  uap;        /* expected UAP for btbb_decode_header (:1211) */
+	uint8_t  whitened;   /* BTBB_WHITENED flag (:663) */
+	uint8_t  type;       /* pkt->packet_type as set by the caller; used only by modes >= 2 */
+	uint8_t  pad;
+	uint32_t reserved;   /* keeps the record 24 bytes without implicit padding */
+} btbb_b200_pkt_in;
+
+/* decode modes */
+#define BTBB_B200_MODE_DECODE      0   /* btbb_decode_header + btbb_decode_payload (:1198-1297) */
+#define BTBB_B200_MODE_TRY_CLOCKS  1   /* try_clock + crc_check for CLK1-6 = 0..63 (:1178-1195, :708-769) */
+#define BTBB_B200_MODE_PAYLOAD     2   /* btbb_decode_payload alone, packet_type/UAP/clkn as given (:1223-1297) */
+#define BTBB_B200_MODE_CRC_CHECK   3   /* crc_check(clkn & 63, pkt) alone, packet_type/UAP as given (:708-769) */
+#define BTBB_B200_MODE_RAW         16  /* + n: one type decoder without crc_check's post-filter:
+                                          0 fhs, 1 DM, 2 DH, 3 EV3, 4 EV4, 5 EV5, 6 HV (:783-1174) */
+
+typedef struct btbb_b200_ctx btbb_b200_ctx;
+
+/* Library / device bring-up.  Replaces btbb_init() (bluetooth_packet.c:279-292): builds the
+ * syndrome -> error tables for 1..max_ac_errors bit errors on `device` and uploads the
+ * constant tables.  max_ac_errors outside [0,5] -> BTBB_B200_EINVAL.  */
+int  btbb_b200_create(int device, int max_ac_errors, btbb_b200_ctx **ctx);
+void btbb_b200_destroy(btbb_b200_ctx *ctx);
+int  btbb_b200_device(const btbb_b200_ctx *ctx);
+int  btbb_b200_table_errors(const btbb_b200_ctx *ctx);   /* the k the tables were built for */
+const char *btbb_b200_last_error(void);
+
+/*
+ * Batch btbb_find_ac (bluetooth_packet.c:444-464) over a DEVICE-resident stream of one byte
+ * per symbol (values 0/1), reporting EVERY position in [0, search_length) that the
+ * reference would report when iterated with restart at offset+1, in ascending offset order.
+ *   lap == BTBB_B200_LAP_ANY -> promiscuous_packet_search semantics (:368-420)
+ *   otherwise                -> find_known_lap semantics (:423-441)
+ * d_stream must hold search_length + 63 readable symbols (the header asks for +72, btbb.h:82).
+ * d_hits has room for max_hits records; *n_hits receives the total found (may exceed max_hits,
+ * in which case BTBB_B200_EOVERFLOW is returned and the first max_hits records are valid).
+ * All work is enqueued on cuda_stream (a cudaStream_t passed as void*; NULL = default stream);
+ * the call synchronises that stream before returning.
+ */
+int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+			  uint32_t lap, int max_ac_errors,
+			  btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits,
+			  void *cuda_stream);
+
+/* Same, but only enqueues the scan kernel(s) (no synchronisation, no ordering pass);
+ * used by the benchmark to time the kernel alone.  d_count is a device int64 counter
+ * of the hits (unordered), zeroed by the call itself on the same stream. */
+int btbb_b200_find_ac_enqueue(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+			      uint32_t lap, int max_ac_errors,
+			      btbb_b200_hit *d_hits, int64_t max_hits, unsigned long long *d_count,
+			      void *cuda_stream);
+
+/* Host-buffer form: copies the stream to the device in chunks (double-buffered, pinned
+ * staging), scans, and returns sorted hits in host memory.  This is what the classic
+ * btbb_find_ac() shim calls. */
+int btbb_b200_find_ac_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_length,
+			   uint32_t lap, int max_ac_errors,
+			   btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits);
+
+/*
+ * Batch per-packet chain.  BTBB_B200_MODE_DECODE uses the packet's own clkn/UAP; d_out
+ * holds n records.  BTBB_B200_MODE_TRY_CLOCKS is the inner loop of
+ * bluetooth_piconet.c:675-689; d_out holds n*64 records, record [p*64+c] for packet p,
+ * clock c.  The other modes serve the single-function entry points of the classic API.  Symbols at index >= length read as 0 (a freshly calloc'ed
+ * btbb_packet, bluetooth_packet.c:297).
+ */
+int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+			 const btbb_b200_pkt_in *d_pkts, int64_t n, int mode,
+			 btbb_b200_decoded *d_out, void *cuda_stream);
+
+int btbb_b200_decode_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
+			  const btbb_b200_pkt_in *pkts, int64_t n, int mode,
+			  btbb_b200_decoded *out);
+
+/* btbb_header_present (bluetooth_packet.c:1371-1408) for n packets; d_present[n] gets 0/1. */
+int btbb_b200_header_present_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+				 const btbb_b200_pkt_in *d_pkts, int64_t n,
+				 uint8_t *d_present, void *cuda_stream);
+
+/* ---- synthetic capture generator (SURVEY.md 8d "Synthetic input"; test/bench data only) ---- */
+typedef struct btbb_b200_synth_cfg {
+	uint64_t seed;          /* 0xB200B7BB by default */
+	int64_t  n_symbols;     /* total symbols to generate (the buffer must hold this many bytes) */
+	int64_t  first_symbol;  /* global index of buffer[0] (lets each rank generate its own shard) */
+	int32_t  stride;        /* one planted packet per `stride` symbols; 0 = noise only */
+	int32_t  n_laps;        /* planted LAPs are drawn from a table of this many (1..64) */
+	uint32_t ber_q32;       /* bit-flip probability * 2^32 applied to every symbol */
+	uint32_t packet_mix;    /* bit i set => packet kind i may be planted (see BTBB_B200_KIND_*) */
+	uint32_t fixed_lap;     /* if n_laps == 1: the LAP to plant */
+	uint32_t reserved;
+} btbb_b200_synth_cfg;
+
+#define BTBB_B200_KIND_ID    0   /* 68-symbol ID packet: access code only */
+#define BTBB_B200_KIND_DM1   1
+#define BTBB_B200_KIND_DH1   2
+#define BTBB_B200_KIND_DM3   3
+#define BTBB_B200_KIND_FHS   4
+#define BTBB_B200_KIND_HV1   5
+#define BTBB_B200_KIND_DM5   6
+#define BTBB_B200_KIND_DH3   7
+#define BTBB_B200_KIND_COUNT 8
+
+/* Ground truth for planted packet `slot` (same on host and device). */
+typedef struct btbb_b200_planted {
+	int64_t  offset;     /* symbol index of the sync word */
+	uint32_t lap;
+	uint8_t  uap;
+	uint8_t  kind;
+	uint8_t  clk6;       /* whitening clock CLK1-6 */
+	uint8_t  lt_addr;
+	int32_t  n_symbols;  /* packet length in symbols from the sync word (68 for ID) */
+	int32_t  body_bytes; /* payload body length */
+} btbb_b200_planted;
+
+int btbb_b200_synth_host(const btbb_b200_synth_cfg *cfg, uint8_t *buffer);
+int btbb_b200_synth_dev(const btbb_b200_synth_cfg *cfg, uint8_t *d_buffer, void *cuda_stream);
+int btbb_b200_synth_planted(const btbb_b200_synth_cfg *cfg, int64_t slot, btbb_b200_planted *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTBB_B200_H */

@@ -1,0 +1,178 @@
+"""ctypes view of the C ABI in include/btbb_b200.h (tests and bench.py use this; the
+product itself is the shared object).  Importing never falls back to anything: if
+libbtbb.so.1 is missing the import raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libbtbb.so.1")
+LAP_ANY = 0xFFFFFFFF
+
+
+class Hit(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("lap", C.c_uint32), ("ac_errors", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class Decoded(C.Structure):
+    _fields_ = [("header_ok", C.c_int32), ("rv", C.c_int32), ("uap", C.c_uint8), ("type", C.c_uint8),
+                ("lt_addr", C.c_uint8), ("flags", C.c_uint8), ("hec", C.c_uint8), ("llid", C.c_uint8),
+                ("flow", C.c_uint8), ("has_payload", C.c_uint8), ("payload_header_length", C.c_int32),
+                ("payload_length", C.c_int32), ("header_packed", C.c_uint32), ("payload", C.c_uint8 * 344)]
+
+
+class PktIn(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("length", C.c_int32), ("clkn", C.c_uint32), ("uap", C.c_uint8),
+                ("whitened", C.c_uint8), ("type", C.c_uint8), ("pad", C.c_uint8), ("reserved", C.c_uint32)]
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_symbols", C.c_int64), ("first_symbol", C.c_int64),
+                ("stride", C.c_int32), ("n_laps", C.c_int32), ("ber_q32", C.c_uint32),
+                ("packet_mix", C.c_uint32), ("fixed_lap", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Planted(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("lap", C.c_uint32), ("uap", C.c_uint8), ("kind", C.c_uint8),
+                ("clk6", C.c_uint8), ("lt_addr", C.c_uint8), ("n_symbols", C.c_int32), ("body_bytes", C.c_int32)]
+
+
+HIT_DTYPE = np.dtype([("offset", "<i8"), ("lap", "<u4"), ("ac_errors", "u1"), ("pad", "u1", (3,))])
+DECODED_DTYPE = np.dtype([("header_ok", "<i4"), ("rv", "<i4"), ("uap", "u1"), ("type", "u1"), ("lt_addr", "u1"),
+                          ("flags", "u1"), ("hec", "u1"), ("llid", "u1"), ("flow", "u1"), ("has_payload", "u1"),
+                          ("payload_header_length", "<i4"), ("payload_length", "<i4"), ("header_packed", "<u4"),
+                          ("payload", "u1", (344,))])
+PKTIN_DTYPE = np.dtype([("offset", "<i8"), ("length", "<i4"), ("clkn", "<u4"), ("uap", "u1"),
+                        ("whitened", "u1"), ("type", "u1"), ("pad", "u1"), ("reserved", "<u4")])
+assert HIT_DTYPE.itemsize == C.sizeof(Hit) == 16
+assert DECODED_DTYPE.itemsize == C.sizeof(Decoded) == 372
+assert PKTIN_DTYPE.itemsize == C.sizeof(PktIn) == 24
+
+KIND = {"ID": 0, "DM1": 1, "DH1": 2, "DM3": 3, "FHS": 4, "HV1": 5, "DM5": 6, "DH3": 7}
+DEFAULT_SEED = 0xB200B7BB
+
+_vp, _i64, _u32, _int = C.c_void_p, C.c_int64, C.c_uint32, C.c_int
+_PROTOS = {
+    "btbb_b200_create": (_int, [_int, _int, C.POINTER(_vp)]),
+    "btbb_b200_destroy": (None, [_vp]),
+    "btbb_b200_device": (_int, [_vp]),
+    "btbb_b200_table_errors": (_int, [_vp]),
+    "btbb_b200_last_error": (C.c_char_p, []),
+    "btbb_b200_find_ac_dev": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64), _vp]),
+    "btbb_b200_find_ac_enqueue": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, _vp, _vp]),
+    "btbb_b200_find_ac_host": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64)]),
+    "btbb_b200_decode_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
+    "btbb_b200_decode_host": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp]),
+    "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "btbb_b200_synth_host": (_int, [C.POINTER(SynthCfg), _vp]),
+    "btbb_b200_synth_dev": (_int, [C.POINTER(SynthCfg), _vp, _vp]),
+    "btbb_b200_synth_planted": (_int, [C.POINTER(SynthCfg), _i64, C.POINTER(Planted)]),
+}
+# the classic surface (include/btbb.h) -- checked for presence by tests/test_abi.py
+CLASSIC_SYMBOLS = [
+    "btbb_init", "btbb_get_release", "btbb_get_version", "btbb_packet_new", "btbb_packet_ref",
+    "btbb_packet_unref", "btbb_find_ac", "btbb_packet_set_flag", "btbb_packet_get_flag",
+    "btbb_packet_get_lap", "btbb_packet_set_uap", "btbb_packet_get_uap", "btbb_packet_get_nap",
+    "btbb_packet_set_modulation", "btbb_packet_set_transport", "btbb_packet_get_modulation",
+    "btbb_packet_get_transport", "btbb_packet_get_channel", "btbb_packet_get_ac_errors",
+    "btbb_packet_get_clkn", "btbb_packet_get_header_packed", "btbb_packet_set_data", "btbb_get_symbols",
+    "btbb_packet_get_payload_length", "btbb_get_payload", "btbb_get_payload_packed", "btbb_packet_get_type",
+    "btbb_packet_get_lt_addr", "btbb_packet_get_header_flags", "btbb_packet_get_hec", "btbb_gen_syncword",
+    "btbb_decode_header", "btbb_decode_payload", "btbb_decode", "btbb_print_packet", "btbb_header_present",
+    # exported helpers the reference's piconet layer links against (bluetooth_packet.h:115-144)
+    "try_clock", "crc_check", "fhs", "DM", "DH", "EV3", "EV4", "EV5", "HV", "tun_format",
+    "lap_from_fhs", "uap_from_fhs", "nap_from_fhs", "clock_from_fhs", "find_known_lap",
+    "promiscuous_packet_search",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libbtbb.so.1; raises if it has not been built (python -m libbtbb_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m libbtbb_b200.build` (there is no fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        L.btbb_gen_syncword.restype = C.c_uint64
+        L.btbb_gen_syncword.argtypes = [_int]
+        _lib = L
+    return _lib
+
+
+class BtbbError(RuntimeError):
+    pass
+
+
+def check(rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise BtbbError(f"libbtbb_b200 error {rc}: {lib().btbb_b200_last_error().decode()}")
+    return rc
+
+
+def synth_cfg(n_symbols, stride=10000, n_laps=64, ber=0.0, mix=("DM1", "DM3", "DH1", "FHS"),
+              seed=DEFAULT_SEED, first_symbol=0, fixed_lap=0x9E8B33):
+    m = 0
+    for k in mix:
+        m |= 1 << KIND[k]
+    return SynthCfg(seed=seed, n_symbols=n_symbols, first_symbol=first_symbol, stride=stride, n_laps=n_laps,
+                    ber_q32=min(int(ber * 2 ** 32), 2 ** 32 - 1), packet_mix=m, fixed_lap=fixed_lap, reserved=0)
+
+
+def synth_host(cfg):
+    buf = np.empty(cfg.n_symbols, dtype=np.uint8)
+    check(lib().btbb_b200_synth_host(C.byref(cfg), buf.ctypes.data))
+    return buf
+
+
+def planted(cfg, slot):
+    p = Planted()
+    check(lib().btbb_b200_synth_planted(C.byref(cfg), slot, C.byref(p)))
+    return p
+
+
+class Context:
+    """One CUDA context of the library on one device (btbb_init replacement)."""
+
+    def __init__(self, device=0, max_ac_errors=2):
+        self.h = _vp()
+        check(lib().btbb_b200_create(device, max_ac_errors, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().btbb_b200_destroy(self.h)
+            self.h = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def find_ac_host(self, stream, search_length, lap=LAP_ANY, k=2, max_hits=1 << 20):
+        """stream: uint8 numpy array holding search_length + 63 symbols."""
+        assert stream.dtype == np.uint8 and stream.flags.c_contiguous and len(stream) >= search_length + 63
+        hits = np.zeros(max_hits, dtype=HIT_DTYPE)
+        n = _i64(0)
+        check(lib().btbb_b200_find_ac_host(self.h, stream.ctypes.data, search_length, lap, k,
+                                           hits.ctypes.data, max_hits, C.byref(n)))
+        return hits[: n.value]
+
+    def find_ac_dev(self, d_ptr, search_length, d_hits_ptr, max_hits, lap=LAP_ANY, k=2, stream=0):
+        n = _i64(0)
+        rc = lib().btbb_b200_find_ac_dev(self.h, d_ptr, search_length, lap, k, d_hits_ptr, max_hits,
+                                         C.byref(n), stream)
+        check(rc, allow=(-4,))
+        return n.value, rc
+
+    def decode_host(self, stream, pkts, mode=0):
+        assert stream.dtype == np.uint8 and pkts.dtype == PKTIN_DTYPE
+        out = np.zeros(len(pkts) * (64 if mode == 1 else 1), dtype=DECODED_DTYPE)
+        check(lib().btbb_b200_decode_host(self.h, stream.ctypes.data, len(stream), pkts.ctypes.data, len(pkts),
+                                          mode, out.ctypes.data))
+        return out

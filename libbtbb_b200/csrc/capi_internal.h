@@ -1,0 +1,68 @@
+/* capi_internal.h -- state shared by the translation units of libbtbb.so.1 (B200 build). */
+#ifndef BTBB_B200_CAPI_INTERNAL_H
+#define BTBB_B200_CAPI_INTERNAL_H
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/btbb_b200.h"
+
+/* Tables the access-code scan kernels stage into shared memory. */
+struct bt_scan_tables {
+	uint32_t t_a[256];     /* low 32 syndrome bits of a byte at codeword bits 32..39 */
+	uint32_t t_b[256];     /* ... bits 40..47 */
+	uint32_t t_c[256];     /* ... bits 48..55 */
+	uint32_t t_56;         /* ... bit 56 */
+	uint32_t c_class[2];   /* syndrome of (PN ^ corrected Barker tail) for tail A / tail B */
+	uint32_t pad;
+};
+
+/* syndrome -> error pattern, open addressing in global memory (replaces the uthash map of
+ * bluetooth_packet.c:121-145).  Empty slots have syn == 0 (no error pattern has a zero syndrome). */
+struct bt_err_slot { uint64_t syn, err; };
+
+struct btbb_b200_ctx {
+	int device;
+	int table_k;                 /* tables hold every pattern of 1..table_k errors in bits 0..57 */
+	int sm_count;
+	bt_scan_tables *d_tables;    /* device copy */
+	uint32_t *d_bloom;           /* bitmap over the low 32 syndrome bits of table entries (+ zero) */
+	int bloom_log2;              /* log2(bits) */
+	bt_err_slot *d_err;          /* hash table, capacity 1 << err_log2 (NULL when table_k == 0) */
+	int err_log2;
+	long err_entries;
+	/* scratch owned by the context */
+	unsigned long long *d_count; /* hit counter */
+	btbb_b200_hit *d_tmp;        /* unordered hits before the ordering pass */
+	btbb_b200_hit *d_tmp2;       /* second buffer for the host-buffer entry point */
+	int64_t tmp2_cap;
+	int64_t tmp_cap;
+	uint32_t *d_sort_hist;       /* radix-sort histograms */
+	int64_t sort_hist_cap;
+	uint8_t *d_stage[2];         /* device staging for the host-buffer entry points */
+	int64_t stage_cap;
+	cudaStream_t copy_stream[2];
+};
+
+int btbb_b200_set_error(int code, const char *msg);
+int btbb_b200_cuda_fail(cudaError_t e, const char *where);
+#define BT_CUDA_TRY(call) do { cudaError_t e__ = (call); \
+	if (e__ != cudaSuccess) return btbb_b200_cuda_fail(e__, #call); } while (0)
+
+/* tables.cu */
+int bt_tables_build(btbb_b200_ctx *ctx, int max_ac_errors);
+void bt_tables_free(btbb_b200_ctx *ctx);
+
+/* find_ac.cu */
+int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits);
+int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
+		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
+		   int64_t bias, cudaStream_t st);
+int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t have,
+		 int passes, cudaStream_t st, btbb_b200_hit **result);
+int bt_sort_passes(int64_t span);
+
+/* capi.cu */
+int bt_find_first_host(btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,
+		       int max_ac_errors, btbb_b200_hit *hit, int *found);
+
+#endif

@@ -1,0 +1,515 @@
+/*
+ * find_ac.cu -- K1/K2: the sliding 64-bit access-code correlator on sm_100a.
+ *
+ * Replaces btbb_find_ac (bluetooth_packet.c:444-464) and its two search loops,
+ * find_known_lap (:423-441) and promiscuous_packet_search (:368-420), for a whole
+ * byte-per-symbol stream at once.  The reference tests one window per iteration with a
+ * 64-step byte->bit pack (air_to_host64, :235-242); here
+ *
+ *   phase 1  each thread pulls 2x16 symbols with coalesced 128-bit loads and squeezes
+ *            them to bits (one IMAD per 4 symbols) into a shared-memory bit tile,
+ *   phase 2  each lane owns 32 consecutive window positions and evaluates the cheap
+ *            part of the test for all 32 at once with bit-sliced logic on funnel-shifted
+ *            words (promiscuous: the 7-bit Barker tail within distance 1 of either legal
+ *            tail, BARKER_DISTANCE :55-59; known LAP: at most k mismatches among the
+ *            first 16 sync-word bits),
+ *   phase 3  the surviving ~1/8 (promiscuous) positions get the 32 low syndrome bits from
+ *            shared-memory byte LUTs (gen_syndrome :147-159) and a two-hash Bloom probe of
+ *            the syndrome->error map (find_syndrome :139-145),
+ *   phase 4  the handful of Bloom positives run the exact reference test (full 34-bit
+ *            syndrome, error lookup, error count, LAP extraction :390-416).
+ *
+ * Hits are appended unordered and then radix-sorted by offset, which yields exactly the
+ * ascending list the reference produces when iterated with restart at offset+1.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include "bt_math.h"
+#include "scan_hash.h"
+#include "capi_internal.h"
+
+namespace {
+
+constexpr int QCAP = 512;   /* Bloom-positive queue entries per tile */
+
+struct scan_args {
+	const uint8_t *abase;   /* stream pointer rounded down to 16 bytes */
+	int head;               /* abase[head] is stream[0] (0..15) */
+	int64_t n;              /* search_length */
+	int64_t bias;           /* added to every reported offset (chunked host scans) */
+	int64_t vlen;           /* head + n + 63: virtual symbols readable */
+	int64_t ntiles;
+	int kmax;               /* max_ac_errors */
+	uint64_t ac;            /* known-LAP sync word */
+	uint32_t lap;
+	const bt_scan_tables *tables;
+	const uint32_t *bloom;
+	int bloom_log2;
+	const bt_err_slot *err;
+	int err_log2;
+	btbb_b200_hit *hits;
+	int64_t max_hits;
+	unsigned long long *count;
+};
+
+/* 4 symbols (bytes 0/1) -> 4 bits.  x*0x10204080 drops byte j's bit at 28+j; no two
+ * partial products share a bit position, so no carries. */
+__device__ __forceinline__ uint32_t pack4(uint32_t x) { return (x * 0x10204080u) >> 28; }
+
+__device__ __forceinline__ uint32_t load_pack16(const scan_args &a, int64_t byte0)
+{
+	if (byte0 >= a.head && byte0 + 16 <= a.vlen) {
+		uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.abase + byte0));
+		return pack4(v.x) | (pack4(v.y) << 4) | (pack4(v.z) << 8) | (pack4(v.w) << 12);
+	}
+	uint32_t r = 0;
+	for (int j = 0; j < 16; j++) {
+		int64_t i = byte0 + j;
+		if (i >= a.head && i < a.vlen)
+			r |= (uint32_t)(a.abase[i] & 1u) << j;
+	}
+	return r;
+}
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
+__device__ __forceinline__ void push_hit(const scan_args &a, int64_t off, uint32_t lap, uint32_t nerr)
+{
+	if (a.max_hits < 0) {
+		/* first-hit mode (classic btbb_find_ac): keep the smallest offset; the record rides
+		 * in the low bits of the key so one 64-bit atomicMin carries everything */
+		atomicMin(a.count, ((unsigned long long)(off + a.bias) << 32) | ((unsigned long long)lap << 8) | (nerr & 0xff));
+		return;
+	}
+	unsigned long long slot = atomicAdd(a.count, 1ULL);
+	if ((int64_t)slot < a.max_hits) {
+		btbb_b200_hit h;
+		h.offset = off + a.bias; h.lap = lap; h.ac_errors = (uint8_t)nerr; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+		a.hits[slot] = h;
+	}
+}
+
+/* The reference's per-window decision once the Barker tail is known to pass
+ * (bluetooth_packet.c:387-416), exact. */
+__device__ bool exact_promisc(const scan_args &a, uint64_t w, uint32_t *lap, uint32_t *nerr)
+{
+	uint32_t tail = (uint32_t)(w >> 57);
+	uint64_t fixed = (uint64_t)(__popc((tail ^ BT_BARKER_A) & 0x7f) <= 3 ? BT_BARKER_A : BT_BARKER_B) << 57;
+	uint64_t sw = (w & 0x01ffffffffffffffULL) | fixed;
+	uint64_t syn = bt_syndrome_slow(sw ^ BT_PN);
+	uint32_t e = 0;
+	if (syn) {
+		e = 0xff;
+		if (a.err) {
+			uint64_t mask = ((uint64_t)1 << a.err_log2) - 1, h = bt_err_hash(syn, a.err_log2);
+			for (;;) {
+				bt_err_slot s = a.err[h];
+				if (s.syn == syn) { sw ^= s.err; e = (uint32_t)__popcll(s.err); break; }
+				if (s.syn == 0) break;
+				h = (h + 1) & mask;
+			}
+		}
+	}
+	if ((int)e > a.kmax) return false;
+	*lap = (uint32_t)(sw >> 34) & 0xffffffu;
+	*nerr = e;
+	return true;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) scan_promisc_kernel(const scan_args a)
+{
+	constexpr int TILE = NT * 32;
+	extern __shared__ __align__(16) uint32_t smem[];
+	uint32_t *sbits = smem;                         /* NT + 2 words (+2 pad) */
+	uint32_t *s_ta = sbits + NT + 4;                /* 256 */
+	uint32_t *s_tb = s_ta + 256, *s_tc = s_tb + 256;
+	uint32_t *s_misc = s_tc + 256;                  /* t_56, c_class[2], pad */
+	uint32_t *s_q = s_misc + 4;                     /* QCAP */
+	uint32_t *s_qn = s_q + QCAP;                    /* 2 counters (tile parity) */
+	uint32_t *s_bloom = s_qn + 4;                   /* 1 << (bloom_log2 - 5) */
+	const int tid = threadIdx.x;
+	const int blog = a.bloom_log2;
+
+	for (int i = tid; i < 256; i += NT) { s_ta[i] = a.tables->t_a[i]; s_tb[i] = a.tables->t_b[i]; s_tc[i] = a.tables->t_c[i]; }
+	if (tid == 0) { s_misc[0] = a.tables->t_56; s_misc[1] = a.tables->c_class[0]; s_misc[2] = a.tables->c_class[1]; s_qn[0] = 0; s_qn[1] = 0; }
+	for (int i = tid; i < (1 << (blog - 5)); i += NT) s_bloom[i] = a.bloom[i];
+	__syncthreads();
+	const uint32_t t56 = s_misc[0], cls0 = s_misc[1], cls1 = s_misc[2];
+	uint16_t *sb16 = reinterpret_cast<uint16_t *>(sbits);
+
+	int par = 0;
+	for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, par ^= 1) {
+		const int64_t base = tile * TILE;
+		/* ---- phase 1: symbols -> bit tile ---- */
+		#pragma unroll
+		for (int j = 0; j < 2; j++) {
+			int c = j * NT + tid;
+			sb16[c] = (uint16_t)load_pack16(a, base + 16 * (int64_t)c);
+		}
+		if (tid < 4)
+			sb16[2 * NT + tid] = (uint16_t)load_pack16(a, base + 16 * (int64_t)(2 * NT + tid));
+		if (tid == 0) s_qn[par ^ 1] = 0;
+		__syncthreads();
+
+		/* ---- phase 2: Barker tail filter for 32 positions per lane ---- */
+		const uint32_t w0 = sbits[tid], w1 = sbits[tid + 1], w2 = sbits[tid + 2];
+		/* S_j bit i = symbol (pos_i + 57 + j); mismatch against tail A = 0b0100111 */
+		const uint32_t x0 = ~__funnelshift_r(w1, w2, 25), x1 = ~__funnelshift_r(w1, w2, 26),
+			       x2 = ~__funnelshift_r(w1, w2, 27), x3 = __funnelshift_r(w1, w2, 28),
+			       x4 = __funnelshift_r(w1, w2, 29),  x5 = ~__funnelshift_r(w1, w2, 30),
+			       x6 = __funnelshift_r(w1, w2, 31);
+		const uint32_t s1 = x0 ^ x1 ^ x2, c1 = maj3(x0, x1, x2);
+		const uint32_t s2 = x3 ^ x4 ^ x5, c2 = maj3(x3, x4, x5);
+		const uint32_t c3 = maj3(s1, s2, x6);
+		const uint32_t near_a = ~(c1 | c2 | c3);        /* <= 1 mismatch with tail A */
+		const uint32_t near_b = c1 & c2 & c3;           /* >= 6 mismatches = <= 1 with tail B */
+		uint32_t cand = near_a | near_b;
+		/* positions outside [head, head + n) are not searched */
+		{
+			const int64_t p0 = base + 32 * (int64_t)tid;
+			const int64_t lo = a.head - p0, hi = a.head + a.n - p0;
+			if (lo > 0) cand &= lo >= 32 ? 0u : (0xffffffffu << lo);
+			if (hi < 32) cand &= hi <= 0 ? 0u : (0xffffffffu >> (32 - hi));
+		}
+		/* ---- phase 3: low-32 syndrome + Bloom probe per surviving position ---- */
+		while (cand) {
+			const int q = __ffs(cand) - 1;
+			cand &= cand - 1;
+			const uint32_t lo = __funnelshift_r(w0, w1, q);
+			const uint32_t hi = __funnelshift_r(w1, w2, q);
+			uint32_t s = lo ^ s_ta[hi & 255] ^ s_tb[(hi >> 8) & 255] ^ s_tc[(hi >> 16) & 255];
+			s ^= ((hi >> 24) & 1) ? t56 : 0u;
+			s ^= ((near_b >> q) & 1) ? cls1 : cls0;
+			const uint32_t h1 = bt_bloom_h1(s, blog);
+			if ((s_bloom[h1 >> 5] >> (h1 & 31)) & 1) {
+				const uint32_t h2 = bt_bloom_h2(s, blog);
+				if ((s_bloom[h2 >> 5] >> (h2 & 31)) & 1) {
+					const uint32_t rel = 32 * tid + q;
+					const uint32_t slot = atomicAdd(&s_qn[par], 1u);
+					if (slot < QCAP)
+						s_q[slot] = rel;
+					else {  /* queue full (adversarial input): resolve in place */
+						uint64_t w = ((uint64_t)hi << 32) | lo;
+						uint32_t lap, ne;
+						if (exact_promisc(a, w, &lap, &ne))
+							push_hit(a, base + rel - a.head, lap, ne);
+					}
+				}
+			}
+		}
+		__syncthreads();
+		/* ---- phase 4: exact test of the Bloom positives ---- */
+		uint32_t nq = s_qn[par];
+		if (nq > QCAP) nq = QCAP;
+		for (uint32_t i = tid; i < nq; i += NT) {
+			const uint32_t rel = s_q[i], wi = rel >> 5, sh = rel & 31;
+			const uint32_t lo = __funnelshift_r(sbits[wi], sbits[wi + 1], sh);
+			const uint32_t hi = __funnelshift_r(sbits[wi + 1], sbits[wi + 2], sh);
+			uint32_t lap, ne;
+			if (exact_promisc(a, ((uint64_t)hi << 32) | lo, &lap, &ne))
+				push_hit(a, base + rel - a.head, lap, ne);
+		}
+		__syncthreads();
+	}
+}
+
+/* count of set inputs among 16 bit-sliced vectors -> 5 bit planes (carry-save adders) */
+__device__ __forceinline__ void csa16(const uint32_t x[16], uint32_t cnt[5])
+{
+	#define FA(s, c, p, q, r) do { uint32_t p_ = (p), q_ = (q), r_ = (r); s = p_ ^ q_ ^ r_; c = maj3(p_, q_, r_); } while (0)
+	#define HA(s, c, p, q) do { uint32_t p_ = (p), q_ = (q); s = p_ ^ q_; c = p_ & q_; } while (0)
+	uint32_t a0, a1, a2, a3, a4, b0, b1, b2, b3, b4;   /* weight-1 sums a*, weight-2 carries b* */
+	FA(a0, b0, x[0], x[1], x[2]);  FA(a1, b1, x[3], x[4], x[5]);  FA(a2, b2, x[6], x[7], x[8]);
+	FA(a3, b3, x[9], x[10], x[11]); FA(a4, b4, x[12], x[13], x[14]);
+	uint32_t d0, d1, e0, e1;
+	FA(d0, e0, a0, a1, a2); FA(d1, e1, a3, a4, x[15]);
+	uint32_t f0;
+	HA(cnt[0], f0, d0, d1);
+	/* weight 2: b0..b4, e0, e1, f0 */
+	uint32_t g0, g1, h0, h1;
+	FA(g0, h0, b0, b1, b2); FA(g1, h1, b3, b4, e0);
+	uint32_t g2, h2;
+	FA(g2, h2, g0, g1, e1);
+	uint32_t h3;
+	HA(cnt[1], h3, g2, f0);
+	/* weight 4: h0, h1, h2, h3 */
+	uint32_t m0, n0, n1;
+	FA(m0, n0, h0, h1, h2);
+	HA(cnt[2], n1, m0, h3);
+	/* weight 8: n0, n1 */
+	HA(cnt[3], cnt[4], n0, n1);
+	#undef FA
+	#undef HA
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) scan_known_kernel(const scan_args a)
+{
+	constexpr int TILE = NT * 32;
+	__shared__ __align__(16) uint32_t sbits[NT + 4];
+	const int tid = threadIdx.x;
+	uint16_t *sb16 = reinterpret_cast<uint16_t *>(sbits);
+	const uint32_t ac_lo = (uint32_t)a.ac, ac_hi = (uint32_t)(a.ac >> 32);
+	const int kk = a.kmax > 16 ? 16 : (a.kmax < 0 ? -1 : a.kmax);
+
+	for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+		const int64_t base = tile * TILE;
+		#pragma unroll
+		for (int j = 0; j < 2; j++) {
+			int c = j * NT + tid;
+			sb16[c] = (uint16_t)load_pack16(a, base + 16 * (int64_t)c);
+		}
+		if (tid < 4)
+			sb16[2 * NT + tid] = (uint16_t)load_pack16(a, base + 16 * (int64_t)(2 * NT + tid));
+		__syncthreads();
+		const uint32_t w0 = sbits[tid], w1 = sbits[tid + 1], w2 = sbits[tid + 2];
+		/* prefilter: mismatches among sync-word bits 0..15 must already be <= k */
+		uint32_t x[16], cnt[5];
+		#pragma unroll
+		for (int j = 0; j < 16; j++)
+			x[j] = __funnelshift_r(w0, w1, j) ^ (((ac_lo >> j) & 1) ? 0xffffffffu : 0u);
+		csa16(x, cnt);
+		uint32_t less = 0, eq = 0xffffffffu;
+		#pragma unroll
+		for (int i = 4; i >= 0; i--) {
+			const uint32_t kb = (kk >= 0 && ((kk >> i) & 1)) ? 0xffffffffu : 0u;
+			less |= eq & ~cnt[i] & kb;
+			eq &= ~(cnt[i] ^ kb);
+		}
+		uint32_t cand = kk < 0 ? 0u : (less | eq);
+		{
+			const int64_t p0 = base + 32 * (int64_t)tid;
+			const int64_t lo = a.head - p0, hi = a.head + a.n - p0;
+			if (lo > 0) cand &= lo >= 32 ? 0u : (0xffffffffu << lo);
+			if (hi < 32) cand &= hi <= 0 ? 0u : (0xffffffffu >> (32 - hi));
+		}
+		while (cand) {
+			const int q = __ffs(cand) - 1;
+			cand &= cand - 1;
+			const uint32_t lo = __funnelshift_r(w0, w1, q);
+			const uint32_t hi = __funnelshift_r(w1, w2, q);
+			const int d = __popc(lo ^ ac_lo) + __popc(hi ^ ac_hi);
+			if (d <= a.kmax)
+				push_hit(a, base + 32 * (int64_t)tid + q - a.head, a.lap, (uint32_t)(uint8_t)d);
+		}
+		__syncthreads();
+	}
+}
+
+/* ---------------- ordering pass: LSD radix sort of 16-byte hit records by offset ---------------- */
+constexpr int SORT_CHUNK = 2048;   /* records per warp */
+
+__global__ void sort_hist_kernel(const btbb_b200_hit *in, int64_t n, int shift, uint32_t *hist, int nblk)
+{
+	__shared__ uint32_t h[256];
+	for (int i = threadIdx.x; i < 256; i += 32) h[i] = 0;
+	__syncwarp();
+	int64_t b0 = (int64_t)blockIdx.x * SORT_CHUNK, b1 = b0 + SORT_CHUNK < n ? b0 + SORT_CHUNK : n;
+	for (int64_t i = b0 + threadIdx.x; i < b1; i += 32)
+		atomicAdd(&h[(uint32_t)((uint64_t)in[i].offset >> shift) & 255u], 1u);
+	__syncwarp();
+	for (int i = threadIdx.x; i < 256; i += 32) hist[(int64_t)i * nblk + blockIdx.x] = h[i];
+}
+
+/* exclusive scan of `len` counters in place, one block */
+__global__ void sort_scan_kernel(uint32_t *v, int64_t len)
+{
+	__shared__ uint32_t part[1024];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int64_t base = 0; base < len; base += 1024) {
+		int64_t i = base + threadIdx.x;
+		uint32_t x = i < len ? v[i] : 0;
+		part[threadIdx.x] = x;
+		__syncthreads();
+		for (int d = 1; d < 1024; d <<= 1) {
+			uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+			__syncthreads();
+			part[threadIdx.x] += t;
+			__syncthreads();
+		}
+		uint32_t incl = part[threadIdx.x];
+		if (i < len) v[i] = carry + incl - x;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry += incl;
+		__syncthreads();
+	}
+}
+
+__global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out, int64_t n, int shift,
+				    const uint32_t *hist, int nblk)
+{
+	__shared__ uint32_t cur[256];
+	const int lane = threadIdx.x;
+	for (int i = lane; i < 256; i += 32) cur[i] = hist[(int64_t)i * nblk + blockIdx.x];
+	__syncwarp();
+	int64_t b0 = (int64_t)blockIdx.x * SORT_CHUNK, b1 = b0 + SORT_CHUNK < n ? b0 + SORT_CHUNK : n;
+	for (int64_t i0 = b0; i0 < b1; i0 += 32) {
+		int64_t i = i0 + lane;
+		bool live = i < b1;
+		btbb_b200_hit rec;
+		uint32_t dig = 0;
+		if (live) { rec = in[i]; dig = (uint32_t)((uint64_t)rec.offset >> shift) & 255u; }
+		unsigned act = __ballot_sync(0xffffffffu, live);
+		if (live) {
+			unsigned peers = __match_any_sync(act, dig);
+			unsigned rank = __popc(peers & ((1u << lane) - 1));
+			uint32_t basepos = cur[dig];
+			out[basepos + rank] = rec;
+			__syncwarp(act);
+			if (rank == 0) cur[dig] = basepos + __popc(peers);
+		}
+		__syncwarp();
+	}
+}
+
+}  // namespace
+
+int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
+		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
+		   int64_t bias, cudaStream_t st)
+{
+	scan_args a;
+	uintptr_t p = reinterpret_cast<uintptr_t>(d_stream);
+	a.head = (int)(p & 15);
+	a.abase = reinterpret_cast<const uint8_t *>(p - a.head);
+	a.n = n;
+	a.bias = bias;
+	a.vlen = a.head + n + 63;
+	a.kmax = k;
+	a.lap = lap;
+	a.ac = lap == BTBB_B200_LAP_ANY ? 0 : bt_gen_syncword(lap);
+	a.tables = ctx->d_tables;
+	a.bloom = ctx->d_bloom;
+	a.bloom_log2 = ctx->bloom_log2;
+	a.err = ctx->d_err;
+	a.err_log2 = ctx->err_log2;
+	a.hits = d_out;
+	a.max_hits = max_hits;
+	a.count = d_count;
+	if (n <= 0) return BTBB_B200_OK;
+	if (lap == BTBB_B200_LAP_ANY) {
+		size_t bloom_bytes = (size_t)4 << (ctx->bloom_log2 - 5);
+		if (ctx->bloom_log2 <= 17) {
+			constexpr int NT = 256;
+			size_t smem = (NT + 4 + 768 + 4 + QCAP + 4) * 4 + bloom_bytes;
+			a.ntiles = (a.head + n + NT * 32 - 1) / (NT * 32);
+			int cta_per_sm = 0;
+			BT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, scan_promisc_kernel<NT>, NT, smem));
+			if (cta_per_sm < 1) cta_per_sm = 1;
+			int64_t grid = (int64_t)ctx->sm_count * cta_per_sm;
+			if (grid > a.ntiles) grid = a.ntiles;
+			scan_promisc_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(a);
+		} else {
+			constexpr int NT = 1024;
+			size_t smem = (NT + 4 + 768 + 4 + QCAP + 4) * 4 + bloom_bytes;
+			a.ntiles = (a.head + n + NT * 32 - 1) / (NT * 32);
+			BT_CUDA_TRY(cudaFuncSetAttribute(scan_promisc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			int64_t grid = ctx->sm_count;
+			if (grid > a.ntiles) grid = a.ntiles;
+			scan_promisc_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(a);
+		}
+	} else {
+		constexpr int NT = 256;
+		a.ntiles = (a.head + n + NT * 32 - 1) / (NT * 32);
+		int64_t grid = (int64_t)ctx->sm_count * 8;
+		if (grid > a.ntiles) grid = a.ntiles;
+		scan_known_kernel<NT><<<(unsigned)grid, NT, 0, st>>>(a);
+	}
+	BT_CUDA_TRY(cudaGetLastError());
+	return BTBB_B200_OK;
+}
+
+/* LSD radix sort by offset; `a` holds `have` records, `b` is scratch.  *result = the buffer
+ * that ends up sorted (a when the number of passes is even, else b). */
+int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t have,
+		 int passes, cudaStream_t st, btbb_b200_hit **result)
+{
+	btbb_b200_hit *src = a, *dst = b;
+	if (have > 0) {
+		int nblk = (int)((have + SORT_CHUNK - 1) / SORT_CHUNK);
+		for (int p = 0; p < passes; p++) {
+			sort_hist_kernel<<<nblk, 32, 0, st>>>(src, have, 8 * p, ctx->d_sort_hist, nblk);
+			sort_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_sort_hist, (int64_t)nblk * 256);
+			sort_scatter_kernel<<<nblk, 32, 0, st>>>(src, dst, have, 8 * p, ctx->d_sort_hist, nblk);
+			btbb_b200_hit *t = src; src = dst; dst = t;
+		}
+		BT_CUDA_TRY(cudaGetLastError());
+	} else if (passes & 1)
+		src = b;
+	*result = src;
+	return BTBB_B200_OK;
+}
+
+int bt_sort_passes(int64_t span)
+{
+	int bits = 1;
+	while (bits < 63 && ((int64_t)1 << bits) < span) bits++;
+	return (bits + 7) / 8;
+}
+
+int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits)
+{
+	if (hits > ctx->tmp_cap) {
+		if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+		ctx->d_tmp = NULL; ctx->tmp_cap = 0;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_tmp, (size_t)hits * sizeof(btbb_b200_hit)));
+		ctx->tmp_cap = hits;
+	}
+	int64_t nblk = (hits + SORT_CHUNK - 1) / SORT_CHUNK;
+	if (nblk * 256 > ctx->sort_hist_cap) {
+		if (ctx->d_sort_hist) cudaFree(ctx->d_sort_hist);
+		ctx->d_sort_hist = NULL; ctx->sort_hist_cap = 0;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_sort_hist, (size_t)nblk * 256 * sizeof(uint32_t)));
+		ctx->sort_hist_cap = nblk * 256;
+	}
+	return BTBB_B200_OK;
+}
+
+extern "C" int btbb_b200_find_ac_enqueue(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+					 uint32_t lap, int max_ac_errors, btbb_b200_hit *d_hits,
+					 int64_t max_hits, unsigned long long *d_count, void *cuda_stream)
+{
+	if (!ctx || (!d_stream && search_length > 0) || search_length < 0 || max_hits < 0 || !d_count ||
+	    (lap != BTBB_B200_LAP_ANY && lap > 0xffffffu))
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: bad arguments");
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	BT_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), (cudaStream_t)cuda_stream));
+	return bt_scan_launch(ctx, d_stream, search_length, lap, max_ac_errors, d_hits, max_hits, d_count,
+			      0, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+				     uint32_t lap, int max_ac_errors, btbb_b200_hit *d_hits,
+				     int64_t max_hits, int64_t *n_hits, void *cuda_stream)
+{
+	if (!ctx || !n_hits || (!d_hits && max_hits > 0) || (!d_stream && search_length > 0) ||
+	    search_length < 0 || max_hits < 0 || (lap != BTBB_B200_LAP_ANY && lap > 0xffffffu))
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: bad arguments");
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	*n_hits = 0;
+	int rc = bt_ensure_tmp(ctx, max_hits > 0 ? max_hits : 1);
+	if (rc) return rc;
+	/* the scan writes into whichever buffer makes the last scatter land in d_hits */
+	int passes = bt_sort_passes(search_length);
+	btbb_b200_hit *first = (passes & 1) ? ctx->d_tmp : d_hits;
+	btbb_b200_hit *other = (passes & 1) ? d_hits : ctx->d_tmp;
+	BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
+	rc = bt_scan_launch(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, 0, st);
+	if (rc) return rc;
+	unsigned long long total = 0;
+	BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
+	BT_CUDA_TRY(cudaStreamSynchronize(st));
+	*n_hits = (int64_t)total;
+	int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
+	btbb_b200_hit *res = NULL;
+	rc = bt_sort_hits(ctx, first, other, have, passes, st, &res);
+	if (rc) return rc;
+	BT_CUDA_TRY(cudaStreamSynchronize(st));
+	if ((int64_t)total > max_hits)
+		return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
+	return BTBB_B200_OK;
+}

@@ -1,0 +1,96 @@
+/*
+ * tables.cu -- host-side construction of the device tables used by the access-code scan:
+ *   * byte LUTs of the (64,30) code's syndrome (what sw_check_tables.h holds in the
+ *     reference, here derived from g(x) and cut to the low 32 bits for the fast path),
+ *   * the syndrome -> error-pattern map of gen_syndrome_map()/cycle()
+ *     (bluetooth_packet.c:161-185) as an open-addressing table in global memory,
+ *   * a two-hash Bloom bitmap over the map's keys that the kernel keeps in shared memory.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "bt_math.h"
+#include "capi_internal.h"
+#include "scan_hash.h"
+
+static uint64_t g_bit_syn[64];
+
+static void enumerate(std::vector<bt_err_slot> &out, uint64_t err, uint64_t syn, int start, int depth)
+{
+	for (int i = start; i < 58; i++) {      /* errors are confined to bits 0..57 (:167) */
+		uint64_t e = err | (1ULL << i), s = syn ^ g_bit_syn[i];
+		if (depth > 1)
+			enumerate(out, e, s, i + 1, depth - 1);
+		else
+			out.push_back(bt_err_slot{s, e});
+	}
+}
+
+int bt_tables_build(btbb_b200_ctx *ctx, int k)
+{
+	for (int i = 0; i < 64; i++)
+		g_bit_syn[i] = bt_syndrome_slow(1ULL << i);
+
+	/* --- byte LUTs + class constants --- */
+	bt_scan_tables t;
+	memset(&t, 0, sizeof(t));
+	for (int b = 0; b < 256; b++) {
+		uint64_t sa = 0, sb = 0, sc = 0;
+		for (int j = 0; j < 8; j++)
+			if ((b >> j) & 1) { sa ^= g_bit_syn[32 + j]; sb ^= g_bit_syn[40 + j]; sc ^= g_bit_syn[48 + j]; }
+		t.t_a[b] = (uint32_t)sa; t.t_b[b] = (uint32_t)sb; t.t_c[b] = (uint32_t)sc;
+	}
+	t.t_56 = (uint32_t)g_bit_syn[56];
+	t.c_class[0] = (uint32_t)bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_A << 57));
+	t.c_class[1] = (uint32_t)bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
+	BT_CUDA_TRY(cudaMalloc(&ctx->d_tables, sizeof(t)));
+	BT_CUDA_TRY(cudaMemcpy(ctx->d_tables, &t, sizeof(t), cudaMemcpyHostToDevice));
+
+	/* --- error patterns --- */
+	std::vector<bt_err_slot> ents;
+	for (int i = 1; i <= k; i++)
+		enumerate(ents, 0, 0, 0, i);
+	ctx->err_entries = (long)ents.size();
+	ctx->table_k = k;
+
+	/* --- Bloom bitmap over low-32 syndromes (zero syndrome included) --- */
+	int blog = 13;
+	while (blog < 20 && (1L << blog) < 64L * (long)(ents.size() + 1)) blog++;
+	ctx->bloom_log2 = blog;
+	std::vector<uint32_t> bloom((size_t)1 << (blog - 5), 0u);
+	auto bloom_add = [&](uint32_t s32) {
+		uint32_t h1 = bt_bloom_h1(s32, blog), h2 = bt_bloom_h2(s32, blog);
+		bloom[h1 >> 5] |= 1u << (h1 & 31);
+		bloom[h2 >> 5] |= 1u << (h2 & 31);
+	};
+	bloom_add(0);
+	for (auto &e : ents) bloom_add((uint32_t)e.syn);
+	BT_CUDA_TRY(cudaMalloc(&ctx->d_bloom, bloom.size() * sizeof(uint32_t)));
+	BT_CUDA_TRY(cudaMemcpy(ctx->d_bloom, bloom.data(), bloom.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+
+	/* --- open-addressing map --- */
+	ctx->d_err = NULL; ctx->err_log2 = 0;
+	if (!ents.empty()) {
+		int lg = 4;
+		while ((1UL << lg) < 2 * ents.size()) lg++;
+		std::vector<bt_err_slot> tab((size_t)1 << lg, bt_err_slot{0, 0});
+		uint64_t mask = ((uint64_t)1 << lg) - 1;
+		for (auto &e : ents) {
+			uint64_t h = bt_err_hash(e.syn, lg);
+			while (tab[h].syn) h = (h + 1) & mask;
+			tab[h] = e;
+		}
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_err, tab.size() * sizeof(bt_err_slot)));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_err, tab.data(), tab.size() * sizeof(bt_err_slot), cudaMemcpyHostToDevice));
+		ctx->err_log2 = lg;
+	}
+	return BTBB_B200_OK;
+}
+
+void bt_tables_free(btbb_b200_ctx *ctx)
+{
+	if (ctx->d_tables) cudaFree(ctx->d_tables);
+	if (ctx->d_bloom) cudaFree(ctx->d_bloom);
+	if (ctx->d_err) cudaFree(ctx->d_err);
+	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
+}

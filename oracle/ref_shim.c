@@ -1,0 +1,194 @@
+/*
+ * oracle/ref_shim.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Compiles the UNMODIFIED reference translation unit where it lies
+ * (/root/reference/lib/src/bluetooth_packet.c, found through -I) into
+ * oracle/_ref/libbtbb_ref.so and adds thin exported wrappers so tests can
+ * reach its `static` helpers and iterate btbb_find_ac quickly.  No reference
+ * source is copied into this repository: this file only #includes it at
+ * build time ("Reaching static functions").
+ */
+#define RELEASE "2020-12-R1"
+#define VERSION "ref-oracle"
+#include "bluetooth_packet.c"   /* -I/root/reference/lib/src */
+
+#include <string.h>
+#include <pthread.h>
+#include <time.h>
+
+uint64_t ref_gen_syndrome(uint64_t cw) { return gen_syndrome(cw); }
+uint64_t ref_air_to_host64(const char *s, int bits) { return air_to_host64(s, bits); }
+int ref_unfec13(char *in, char *out, int length) { return unfec13(in, out, length); }
+uint16_t ref_fec23(uint16_t data) { return fec23(data); }
+/* returns 1 and fills out[ceil10(length)] on success, 0 when the reference returns NULL */
+int ref_unfec23(char *in, int length, char *out)
+{
+	char *o = unfec23(in, length);
+	int padded = length % 10 ? length + 10 - length % 10 : length;
+	if (!o) return 0;
+	memcpy(out, o, padded);
+	free(o);
+	return 1;
+}
+void ref_unwhiten(char *in, char *out, int clock, int length, int skip, int whitened)
+{
+	btbb_packet p;
+	memset(&p, 0, sizeof(p));
+	btbb_packet_set_flag(&p, BTBB_WHITENED, whitened);
+	unwhiten(in, out, clock, length, skip, &p);
+}
+uint16_t ref_crcgen(char *payload, int length, int uap) { return crcgen(payload, length, uap); }
+uint8_t ref_uap_from_hec(uint16_t data, uint8_t hec) { return uap_from_hec(data, hec); }
+uint8_t ref_reverse(uint8_t b) { return reverse((char)b); }
+int ref_sizeof_packet(void) { return (int)sizeof(btbb_packet); }
+uint8_t ref_barker_distance(int b) { return BARKER_DISTANCE[b & 127]; }
+uint64_t ref_barker_correct(int b) { return barker_correct[b & 127]; }
+uint8_t ref_whitening_bit(int i) { return WHITENING_DATA[i % 127]; }
+uint8_t ref_whitening_index(int clk) { return INDICES[clk & 63]; }
+long ref_syndrome_map_count(void) { return syndrome_map ? (long)HASH_COUNT(syndrome_map) : 0; }
+
+/* One hit record, same layout as btbb_b200_hit (include/btbb_b200.h). */
+typedef struct { int64_t offset; uint32_t lap; uint8_t ac_errors; uint8_t pad[3]; } ref_hit;
+
+/*
+ * Iterate the reference btbb_find_ac over [0, search_length) restarting at
+ * offset+1 after every hit (SURVEY.md 8b "Required extension"): the set of
+ * all positions the reference would report.  Calls are chunked below 2^31.
+ * stream must hold search_length + 63 symbols.  Returns the total number of
+ * hits; at most max_hits are stored.
+ */
+int64_t ref_find_all(char *stream, int64_t search_length, uint32_t lap,
+		     int max_ac_errors, ref_hit *hits, int64_t max_hits)
+{
+	int64_t pos = 0, n = 0;
+	btbb_packet *pkt = btbb_packet_new();
+	while (pos < search_length) {
+		int64_t left = search_length - pos;
+		int chunk = left > (1 << 30) ? (1 << 30) : (int)left;
+		int off = btbb_find_ac(stream + pos, chunk, lap, max_ac_errors, &pkt);
+		if (off < 0) { pos += chunk; continue; }
+		if (n < max_hits) {
+			memset(&hits[n], 0, sizeof(ref_hit));
+			hits[n].offset = pos + off;
+			hits[n].lap = btbb_packet_get_lap(pkt);
+			hits[n].ac_errors = btbb_packet_get_ac_errors(pkt);
+		}
+		n++;
+		pos += (int64_t)off + 1;
+	}
+	btbb_packet_unref(pkt);
+	return n;
+}
+
+/* ---- multi-threaded timing harness (bench.py --impl reference / cpu_baseline) ---- */
+typedef struct {
+	char *stream; int64_t begin, end; uint32_t lap; int k; int64_t hits;
+} ref_job;
+
+static void *ref_worker(void *arg)
+{
+	ref_job *j = (ref_job *)arg;
+	ref_hit dummy;
+	j->hits = ref_find_all(j->stream + j->begin, j->end - j->begin, j->lap, j->k, &dummy, 0);
+	return NULL;
+}
+
+/*
+ * Contiguous-chunk partition of [0, search_length) over `threads` pthreads
+ * (the reference is re-entrant after btbb_init: syndrome_map is read-only).
+ * Returns elapsed seconds; *total_hits gets the hit count.
+ */
+double ref_find_all_mt(char *stream, int64_t search_length, uint32_t lap,
+		       int max_ac_errors, int threads, int64_t *total_hits)
+{
+	pthread_t tid[256];
+	ref_job job[256];
+	struct timespec t0, t1;
+	int t;
+	if (threads < 1) threads = 1;
+	if (threads > 256) threads = 256;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	for (t = 0; t < threads; t++) {
+		job[t].stream = stream;
+		job[t].begin = search_length * t / threads;
+		job[t].end = search_length * (t + 1) / threads;
+		job[t].lap = lap; job[t].k = max_ac_errors; job[t].hits = 0;
+		pthread_create(&tid[t], NULL, ref_worker, &job[t]);
+	}
+	*total_hits = 0;
+	for (t = 0; t < threads; t++) { pthread_join(tid[t], NULL); *total_hits += job[t].hits; }
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---- per-packet chain, silent (btbb_decode prints; call the two halves) ---- */
+typedef struct {
+	int32_t header_ok;       /* btbb_decode_header return */
+	int32_t rv;              /* btbb_decode_payload return (0 when header fails) */
+	uint8_t uap, type, lt_addr, flags, hec, llid, flow, has_payload;
+	int32_t payload_header_length;
+	int32_t payload_length;
+	uint32_t header_packed;
+	uint8_t payload[344];    /* packed bytes, payload_length of them */
+} ref_decoded;
+
+static void fill_decoded(btbb_packet *p, ref_decoded *out)
+{
+	int i;
+	out->uap = p->UAP; out->type = p->packet_type; out->lt_addr = p->packet_lt_addr;
+	out->flags = p->packet_flags; out->hec = p->packet_hec;
+	out->llid = p->payload_llid; out->flow = p->payload_flow;
+	out->has_payload = (uint8_t)btbb_packet_get_flag(p, BTBB_HAS_PAYLOAD);
+	out->payload_header_length = p->payload_header_length;
+	out->payload_length = p->payload_length;
+	out->header_packed = btbb_packet_get_header_packed(p);
+	/* payload is defined (include/btbb_b200.h) as the packed bytes when rv >= 2, else zero */
+	if (out->rv >= 2 && p->payload_length > 0 && p->payload_length <= 344)
+		for (i = 0; i < p->payload_length; i++)
+			out->payload[i] = air_to_host8(&p->payload[i * 8], 8);
+}
+
+void ref_decode_one(char *symbols, int length, uint32_t clkn, uint8_t uap, int whitened, ref_decoded *out)
+{
+	btbb_packet *p = btbb_packet_new();
+	int i;
+	memset(out, 0, sizeof(*out));
+	p->LAP = 0; p->flags = 0;
+	btbb_packet_set_flag(p, BTBB_WHITENED, whitened);
+	btbb_packet_set_data(p, symbols, length, 0, clkn << 1);
+	btbb_packet_set_uap(p, uap);
+	btbb_packet_set_flag(p, BTBB_CLK6_VALID, 1);
+	btbb_packet_set_flag(p, BTBB_HAS_PAYLOAD, 0);
+	out->header_ok = btbb_decode_header(p);
+	if (out->header_ok)
+		out->rv = btbb_decode_payload(p);
+	fill_decoded(p, out);
+	btbb_packet_unref(p);
+}
+
+/* try_clock + crc_check for one clock candidate (SURVEY 3.4 inner loop) */
+void ref_try_clock_one(char *symbols, int length, int clock, int whitened, ref_decoded *out)
+{
+	btbb_packet *p = btbb_packet_new();
+	char h[18];
+	int i;
+	memset(out, 0, sizeof(*out));
+	p->flags = 0;
+	btbb_packet_set_flag(p, BTBB_WHITENED, whitened);
+	btbb_packet_set_data(p, symbols, length, 0, 0);
+	out->header_ok = unfec13(p->symbols + 68, h, 18);
+	try_clock(clock, p);
+	out->rv = crc_check(clock, p);
+	fill_decoded(p, out);
+	btbb_packet_unref(p);
+}
+
+int ref_header_present(char *symbols, int length)
+{
+	btbb_packet *p = btbb_packet_new();
+	int r;
+	btbb_packet_set_data(p, symbols, length, 0, 0);
+	r = btbb_header_present(p);
+	btbb_packet_unref(p);
+	return r;
+}
