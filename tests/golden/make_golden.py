@@ -1,0 +1,178 @@
+"""Regenerate the golden fixtures from the UNMODIFIED reference (oracle/_ref/libbtbb_ref.so).
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Inputs are deterministic (numpy PCG64 with fixed seeds, or this repo's own synthetic
+capture generator); every OUTPUT in the fixtures comes from the reference's code.  The
+reference builds its syndrome map once per process (bluetooth_packet.c:288), so each
+btbb_init(k) variant is produced in its own subprocess.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+import util  # noqa: E402
+from util import B  # noqa: E402
+
+
+def find_ac_stream(seed, n):
+    """noise + planted sync words with 0..4 errors, some for LAP 0x9e8b33"""
+    rng = np.random.default_rng(seed)
+    s = rng.integers(0, 2, n + 64, dtype=np.uint8)
+    util.plant_syncwords(s, rng, 150, 4)
+    util.plant_syncwords(s, rng, 60, 6, laps=[0x9E8B33])
+    return s
+
+
+def synth_stream(ber):
+    cfg = B.synth_cfg(600_000, stride=4096, ber=ber, seed=0xB200B7BB + int(ber * 1e4),
+                      mix=("ID", "DM1", "DH1", "DM3", "FHS", "HV1", "DM5", "DH3"))
+    return cfg, B.synth_host(cfg)
+
+
+def gen_find(k_init):
+    R = util.ref()
+    assert R.btbb_init(k_init) == 0
+    out = {"k_init": k_init, "cases": []}
+    N = 1 << 20
+    s = find_ac_stream(1234, N)
+    for lap, ks in ((B.LAP_ANY, range(0, 6)), (0x9E8B33, (0, 1, 2, 5, 9))):
+        for k in ks:
+            h = util.find_all(R, "ref", s, N, lap, k)
+            out["cases"].append({"stream": "rand1234", "n": N, "lap": lap, "k": k, "count": len(h),
+                                 "sha256": util.digest(h), "head": h[:8].tobytes().hex()})
+    cfg, s2 = synth_stream(0.005)
+    n2 = len(s2) - 63
+    for k in range(0, 5):
+        h = util.find_all(R, "ref", s2, n2, B.LAP_ANY, k)
+        out["cases"].append({"stream": "synth0.005", "n": n2, "lap": B.LAP_ANY, "k": k, "count": len(h),
+                             "sha256": util.digest(h), "head": h[:8].tobytes().hex()})
+    return out
+
+
+def gen_primitives():
+    R = util.ref()
+    rng = np.random.default_rng(99)
+    g = {}
+    cws = [int(x) for x in rng.integers(0, 1 << 63, 256, dtype=np.uint64)] + [0xcc7b7268ff614e1b, 0xcc7d7268ff614e1b]
+    g["syndrome"] = [[hex(c), hex(R.ref_gen_syndrome(c))] for c in cws]
+    laps = [0, 0xffffff, 0x9e8b33] + [int(x) for x in rng.integers(0, 1 << 24, 200)]
+    g["syncword"] = [[l, hex(R.btbb_gen_syncword(l))] for l in laps]
+    g["barker_distance"] = [int(R.ref_barker_distance(b)) for b in range(128)]
+    g["barker_correct"] = [hex(R.ref_barker_correct(b)) for b in range(128)]
+    g["whitening"] = []
+    for clk in range(64):
+        bits = [int(R.ref_whitening_bit(int(R.ref_whitening_index(clk)) + i)) for i in range(127)]
+        g["whitening"].append("".join(map(str, bits)))
+    g["fec23"] = [int(R.ref_fec23(d)) for d in range(1024)]
+    g["uap_from_hec"] = [[d, h, int(R.ref_uap_from_hec(d, h))] for d, h in
+                         zip(rng.integers(0, 1024, 300).tolist(), rng.integers(0, 256, 300).tolist())]
+    crc = []
+    for _ in range(100):
+        n = int(rng.integers(0, 300))
+        bits = rng.integers(0, 2, max(n, 1), dtype=np.uint8)
+        uap = int(rng.integers(0, 256))
+        crc.append(["".join(map(str, bits[:n])), uap, int(R.ref_crcgen(bits.ctypes.data_as(C.c_char_p), n, uap))])
+    g["crc"] = crc
+    f13 = []
+    for _ in range(100):
+        L = int(rng.choice([18, 80, 7]))
+        bits = np.repeat(rng.integers(0, 2, L, dtype=np.uint8), 3)
+        flips = rng.random(3 * L) < rng.choice([0.0, 0.05, 0.12])
+        bits ^= flips.astype(np.uint8)
+        out = np.zeros(L, dtype=np.uint8)
+        ok = R.ref_unfec13(bits.ctypes.data_as(C.c_char_p), out.ctypes.data_as(C.c_char_p), L)
+        f13.append(["".join(map(str, bits)), L, int(ok), "".join(map(str, out))])
+    g["unfec13"] = f13
+    f23 = []
+    for _ in range(300):
+        L = int(rng.choice([1, 8, 10, 16, 25, 160]))
+        nb = (L + 9) // 10
+        sym = []
+        for _b in range(nb):
+            cw = int(R.ref_fec23(int(rng.integers(0, 1024))))
+            for e in rng.choice(15, int(rng.choice([0, 0, 1, 1, 2])), replace=False):
+                cw ^= 1 << int(e)
+            sym += [(cw >> i) & 1 for i in range(15)]
+        a = np.array(sym, dtype=np.uint8)
+        out = np.zeros(nb * 10, dtype=np.uint8)
+        ok = R.ref_unfec23(a.ctypes.data_as(C.c_char_p), L, out.ctypes.data_as(C.c_char_p))
+        f23.append(["".join(map(str, sym)), L, int(ok), "".join(map(str, out)) if ok else ""])
+    g["unfec23"] = f23
+    g["sizeof_packet"] = int(R.ref_sizeof_packet())
+    return g
+
+
+def gen_decode():
+    R = util.ref()
+    out = {"streams": []}
+    for ber in (0.0, 0.004, 0.02):
+        cfg, s = synth_stream(ber)
+        recs, tc, hp = [], [], []
+        pl = util.planted_list(cfg)
+        for p in pl:
+            L = min(3125, len(s) - p.offset)
+            recs.append(util.decode_one(R, "ref", s, p.offset, L, p.clk6, p.uap))
+            hp.append(int(R.ref_header_present(s[p.offset:].ctypes.data, L)))
+        for p in pl[:40]:
+            L = min(3125, len(s) - p.offset)
+            for c in range(64):
+                tc.append(util.try_clock_one(R, "ref", s, p.offset, L, c))
+        # truncated packets and a wrong clock / wrong UAP
+        odd = []
+        for p in pl[:60]:
+            for L in (100, 121, 122, 130, 137, 200, 361, 362, 500):
+                odd.append(util.decode_one(R, "ref", s, p.offset, min(L, len(s) - p.offset), p.clk6, p.uap))
+            odd.append(util.decode_one(R, "ref", s, p.offset, 3125, (p.clk6 + 1) & 63, p.uap))
+            odd.append(util.decode_one(R, "ref", s, p.offset, 3125, p.clk6, (p.uap + 1) & 255))
+            odd.append(util.decode_one(R, "ref", s, p.offset, 3125, p.clk6, p.uap, 0))
+        recs, tc, odd = np.array(recs), np.array(tc), np.array(odd)
+        out["streams"].append({
+            "ber": ber, "n_packets": len(pl), "decode_sha256": util.digest(recs),
+            "rv_hist": {str(k): int(v) for k, v in zip(*np.unique(recs["rv"], return_counts=True))},
+            "try_clock_sha256": util.digest(tc), "odd_sha256": util.digest(odd),
+            "header_present": "".join(map(str, hp)),
+            "decode_head": recs[:4].tobytes().hex()})
+    return out
+
+
+def gen_noise_types():
+    """Every packet type, including EV3/EV4/EV5/HV2/DV/AUX1 which the synthetic transmitter
+    does not build: try_clock + crc_check on random symbols lands on all 16 types."""
+    R = util.ref()
+    rng = np.random.default_rng(4242)
+    recs = []
+    for i in range(300):
+        sym = rng.integers(0, 2, 3125, dtype=np.uint8)
+        # make the header triplets agree so unfec13 succeeds
+        hdr = np.repeat(rng.integers(0, 2, 18, dtype=np.uint8), 3)
+        sym[68:122] = hdr
+        L = int(rng.choice([3125, 1500, 700, 400, 250, 140]))
+        for c in range(0, 64, 7):
+            recs.append(util.try_clock_one(R, "ref", sym, 0, L, c))
+        recs.append(util.decode_one(R, "ref", sym, 0, L, int(rng.integers(0, 64)), 0))
+    recs = np.array(recs)
+    return {"seed": 4242, "count": len(recs), "sha256": util.digest(recs),
+            "type_hist": {str(k): int(v) for k, v in zip(*np.unique(recs["type"], return_counts=True))},
+            "rv_hist": {str(k): int(v) for k, v in zip(*np.unique(recs["rv"], return_counts=True))}}
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "find":
+        print(json.dumps(gen_find(int(sys.argv[2]))))
+        sys.exit(0)
+    finds = []
+    for k in (0, 1, 2, 3, 4):
+        r = subprocess.run([sys.executable, __file__, "find", str(k)], capture_output=True, text=True, check=True)
+        finds.append(json.loads(r.stdout))
+    json.dump(finds, open(os.path.join(HERE, "find_ac.json"), "w"), indent=0)
+    json.dump(gen_primitives(), open(os.path.join(HERE, "primitives.json"), "w"), indent=0)
+    json.dump(gen_decode(), open(os.path.join(HERE, "decode.json"), "w"), indent=0)
+    json.dump(gen_noise_types(), open(os.path.join(HERE, "noise_types.json"), "w"), indent=0)
+    print("golden fixtures written to", HERE)

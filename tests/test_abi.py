@@ -1,0 +1,48 @@
+"""The C-ABI shared object loads on a machine without a GPU and exports every symbol that
+include/btbb_b200.h and include/btbb.h declare.  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import util
+from util import B
+
+
+def declared(header):
+    txt = open(os.path.join(util.ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(btbb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_exports_every_declared_symbol(product_lib):
+    names = declared("btbb_b200.h") + declared("btbb.h") + B.CLASSIC_SYMBOLS
+    assert len(names) > 60
+    missing = [n for n in names if not hasattr(product_lib, n)]
+    assert missing == []
+
+
+def test_soname_and_record_layouts(product_lib):
+    import subprocess
+    out = subprocess.run(["readelf", "-d", B.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libbtbb.so.1" in out
+    assert C.sizeof(B.Hit) == 16 and C.sizeof(B.Decoded) == 372 and C.sizeof(B.PktIn) == 24
+
+
+def test_argument_validation_without_gpu(product_lib):
+    h = C.c_void_p()
+    assert product_lib.btbb_b200_create(0, 6, C.byref(h)) == -1      # same range as btbb_init (:282)
+    assert product_lib.btbb_b200_create(0, -1, C.byref(h)) == -1
+    assert b"max_ac_errors" in product_lib.btbb_b200_last_error()
+    assert product_lib.btbb_gen_syncword(0x9e8b33) == 0x4e7a2cce331a3ae2   # pure host helper
+
+
+def test_fails_loudly_without_cuda(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = product_lib.btbb_b200_create(0, 2, C.byref(h))
+    assert rc == -2 and not h.value            # no CPU fallback: creation fails
+    assert b"no CUDA device" in product_lib.btbb_b200_last_error()

@@ -1,0 +1,132 @@
+"""Shared helpers for the test-suite: ctypes views of the oracle (CPU restatement), the
+compiled reference (oracle/_ref, optional) and the product library."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from libbtbb_b200 import binding as B  # noqa: E402
+
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libbtbb_ref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "oracle.h")]
+        if not os.path.exists(ORACLE_SO) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in src):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
+        L = C.CDLL(ORACLE_SO)
+        L.orc_syndrome.restype = C.c_uint64
+        L.orc_syndrome.argtypes = [C.c_uint64]
+        L.orc_gen_syncword.restype = C.c_uint64
+        L.orc_gen_syncword.argtypes = [C.c_uint32]
+        L.orc_barker_correct.restype = C.c_uint64
+        L.orc_find_all.restype = C.c_int64
+        L.orc_find_all.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_void_p, C.c_int64]
+        L.orc_find_all_mt.restype = C.c_double
+        L.orc_find_all_mt.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.orc_fec23.restype = C.c_uint16
+        L.orc_crc16.restype = C.c_uint16
+        L.orc_hec.restype = C.c_uint8
+        L.orc_uap_from_hec.restype = C.c_uint8
+        L.orc_table_entries.restype = C.c_long
+        L.orc_decode_one.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
+        L.orc_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_header_present.argtypes = [C.c_void_p, C.c_int]
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    """The unmodified reference compiled by oracle/Makefile (only where it was built)."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        L.ref_gen_syndrome.restype = C.c_uint64
+        L.ref_gen_syndrome.argtypes = [C.c_uint64]
+        L.btbb_gen_syncword.restype = C.c_uint64
+        L.ref_barker_correct.restype = C.c_uint64
+        L.ref_barker_distance.restype = C.c_uint8
+        L.ref_find_all.restype = C.c_int64
+        L.ref_find_all.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_void_p, C.c_int64]
+        L.ref_find_all_mt.restype = C.c_double
+        L.ref_find_all_mt.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.ref_fec23.restype = C.c_uint16
+        L.ref_crcgen.restype = C.c_uint16
+        L.ref_uap_from_hec.restype = C.c_uint8
+        L.ref_whitening_bit.restype = C.c_uint8
+        L.ref_whitening_index.restype = C.c_uint8
+        L.ref_decode_one.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
+        L.ref_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_header_present.argtypes = [C.c_void_p, C.c_int]
+        _ref = L
+    return _ref
+
+
+def find_all(L, prefix, stream, n, lap, k, cap=1 << 20):
+    """All hits of an oracle-like library (prefix 'orc' or 'ref') as a HIT_DTYPE array."""
+    hits = np.zeros(cap, dtype=B.HIT_DTYPE)
+    cnt = getattr(L, prefix + "_find_all")(stream.ctypes.data, n, lap, k, hits.ctypes.data, cap)
+    assert cnt <= cap
+    return hits[:cnt].copy()
+
+
+def decode_one(L, prefix, stream, off, length, clk, uap, whitened=1):
+    d = np.zeros(1, dtype=B.DECODED_DTYPE)
+    getattr(L, prefix + "_decode_one")(stream[off:].ctypes.data, length, clk, uap, whitened, d.ctypes.data)
+    return d[0]
+
+
+def try_clock_one(L, prefix, stream, off, length, clock, whitened=1):
+    d = np.zeros(1, dtype=B.DECODED_DTYPE)
+    getattr(L, prefix + "_try_clock_one")(stream[off:].ctypes.data, length, clock, whitened, d.ctypes.data)
+    return d[0]
+
+
+def planted_list(cfg):
+    n_slots = (cfg.first_symbol + cfg.n_symbols + cfg.stride - 1) // cfg.stride
+    out = []
+    for s in range(cfg.first_symbol // cfg.stride, n_slots):
+        p = B.planted(cfg, s)
+        if p.offset >= cfg.first_symbol and p.offset + p.n_symbols <= cfg.first_symbol + cfg.n_symbols:
+            out.append(p)
+    return out
+
+
+def digest(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+def plant_syncwords(stream, rng, count, max_errors, laps=None):
+    """Overwrite `count` random places with sync words carrying 0..max_errors bit flips."""
+    O = oracle()
+    placed = []
+    n = len(stream) - 64
+    for _ in range(count):
+        lap = int(rng.choice(laps)) if laps is not None else int(rng.integers(0, 1 << 24))
+        sw = O.orc_gen_syncword(lap)
+        ne = int(rng.integers(0, max_errors + 1))
+        for e in rng.choice(64, ne, replace=False):
+            sw ^= 1 << int(e)
+        p = int(rng.integers(0, n))
+        stream[p:p + 64] = [(sw >> i) & 1 for i in range(64)]
+        placed.append((p, lap, ne))
+    return placed
