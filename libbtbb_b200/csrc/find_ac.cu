@@ -24,6 +24,8 @@
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "bt_math.h"
 #include "scan_hash.h"
 #include "capi_internal.h"
@@ -365,9 +367,11 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 	}
 }
 
+#include "scan_v3.cuh"
+
 }  // namespace
 
-int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
+static int scan_launch_v1(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
 		   int64_t bias, cudaStream_t st)
 {
@@ -420,6 +424,60 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	}
 	BT_CUDA_TRY(cudaGetLastError());
 	return BTBB_B200_OK;
+}
+
+/*
+ * Dispatcher.  The promiscuous scan with tables for k <= 2 runs the warp-autonomous bulk
+ * kernel (scan_v3.cuh) over every whole 4096-symbol strip that starts on a 32-byte
+ * boundary; the unaligned head and the ragged tail go through the tile kernel above, as
+ * do known-LAP scans and the larger error tables.  BTBB_B200_SCAN=v1 forces the tile kernel.
+ */
+int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
+		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
+		   int64_t bias, cudaStream_t st)
+{
+	const char *env = getenv("BTBB_B200_SCAN");
+	const bool force_v1 = env && !strcmp(env, "v1");
+	if (n <= 0) return BTBB_B200_OK;
+	if (lap != BTBB_B200_LAP_ANY || !ctx->d_map2 || force_v1)
+		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
+	const int64_t head = (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);
+	const int64_t nstrips = n > head ? (n - head) / v3::STRIP : 0;
+	if (nstrips < 1)
+		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
+	const int64_t body_end = head + nstrips * v3::STRIP;
+	v3::args a;
+	a.base = d_stream + head;
+	a.pos0 = head;
+	a.nstrips = nstrips;
+	a.lut = ctx->d_lut2;
+	a.map = ctx->d_map2;
+	a.cc[0] = ctx->cc[0]; a.cc[1] = ctx->cc[1];
+	a.m32 = ctx->m32; a.m33 = ctx->m33;
+	memset(&a.common, 0, sizeof(a.common));
+	a.common.bias = bias;
+	a.common.kmax = k;
+	a.common.err = ctx->d_err;
+	a.common.err_log2 = ctx->err_log2;
+	a.common.hits = d_out;
+	a.common.max_hits = max_hits;
+	a.common.count = d_count;
+	static bool attr_set[16];
+	if (ctx->device < 16 && !attr_set[ctx->device]) {
+		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
+		attr_set[ctx->device] = true;
+	}
+	int64_t grid = ctx->sm_count;
+	const int64_t need = (nstrips + v3::WARPS - 1) / v3::WARPS;
+	if (grid > need) grid = need;
+	v3::scan_promisc_v3<<<(unsigned)grid, v3::WARPS * 32, v3::SMEM_BYTES, st>>>(a);
+	BT_CUDA_TRY(cudaGetLastError());
+	int rc = BTBB_B200_OK;
+	if (head > 0)
+		rc = scan_launch_v1(ctx, d_stream, head, lap, k, d_out, max_hits, d_count, bias, st);
+	if (!rc && body_end < n)
+		rc = scan_launch_v1(ctx, d_stream + body_end, n - body_end, lap, k, d_out, max_hits, d_count, bias + body_end, st);
+	return rc;
 }
 
 /* LSD radix sort by offset; `a` holds `have` records, `b` is scratch.  *result = the buffer

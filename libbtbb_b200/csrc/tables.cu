@@ -68,6 +68,47 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	BT_CUDA_TRY(cudaMalloc(&ctx->d_bloom, bloom.size() * sizeof(uint32_t)));
 	BT_CUDA_TRY(cudaMemcpy(ctx->d_bloom, bloom.data(), bloom.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
+	/* --- bulk-kernel tables (scan_v3.cuh): two LUTs over codeword bits 32..44 / 45..56 giving
+	 * the low 32 syndrome bits of the received part, and a single-probe bit map (word = top 14
+	 * bits, bit = low 5) of every value that part can take for an acceptable window: the
+	 * table syndromes (and zero) XOR the constant of either legal tail.  Only built while the
+	 * map stays sparse (k <= 2: at most 3424 of 2^19 bits set). --- */
+	ctx->d_lut2 = NULL; ctx->d_map2 = NULL;
+	ctx->cc[0] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_A << 57));
+	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
+	ctx->m32 = ctx->m33 = 0;
+	for (int j = 0; j < 25; j++) {
+		if ((g_bit_syn[32 + j] >> 32) & 1) ctx->m32 |= 1u << j;
+		if ((g_bit_syn[32 + j] >> 33) & 1) ctx->m33 |= 1u << j;
+	}
+	if (k <= 2) {
+		const int abits = 13, bbits = 12;
+		std::vector<uint32_t> lut(((size_t)1 << abits) + ((size_t)1 << bbits), 0u);
+		for (uint32_t v = 0; v < (1u << abits); v++) {
+			uint64_t sy = 0;
+			for (int j = 0; j < abits; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + j];
+			lut[v] = (uint32_t)sy;
+		}
+		for (uint32_t v = 0; v < (1u << bbits); v++) {
+			uint64_t sy = 0;
+			for (int j = 0; j < bbits; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + abits + j];
+			lut[((size_t)1 << abits) + v] = (uint32_t)sy;
+		}
+		std::vector<uint32_t> map((size_t)1 << (19 - 5), 0u);
+		auto map_add = [&](uint32_t s32) {
+			for (int c = 0; c < 2; c++) {
+				uint32_t v = s32 ^ (uint32_t)ctx->cc[c];
+				map[v >> 18] |= 1u << (v & 31);
+			}
+		};
+		map_add(0);
+		for (auto &e : ents) map_add((uint32_t)e.syn);
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_lut2, lut.size() * sizeof(uint32_t)));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut2, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_map2, map.size() * sizeof(uint32_t)));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_map2, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
+
 	/* --- open-addressing map --- */
 	ctx->d_err = NULL; ctx->err_log2 = 0;
 	if (!ents.empty()) {
@@ -92,5 +133,8 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_tables) cudaFree(ctx->d_tables);
 	if (ctx->d_bloom) cudaFree(ctx->d_bloom);
 	if (ctx->d_err) cudaFree(ctx->d_err);
+	if (ctx->d_lut2) cudaFree(ctx->d_lut2);
+	if (ctx->d_map2) cudaFree(ctx->d_map2);
 	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
+	ctx->d_lut2 = NULL; ctx->d_map2 = NULL;
 }
