@@ -65,6 +65,7 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_tmp) cudaFree(ctx->d_tmp);
 	if (ctx->d_tmp2) cudaFree(ctx->d_tmp2);
 	if (ctx->d_sort_hist) cudaFree(ctx->d_sort_hist);
+	if (ctx->d_xp) cudaFree(ctx->d_xp);
 	for (int i = 0; i < 2; i++) {
 		if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
 		if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
@@ -134,6 +135,8 @@ static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_leng
 	unsigned long long total = 0;
 	BT_CUDA_TRY(cudaMemcpy(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost));
 	if (first_key) { *first_key = total; return BTBB_B200_OK; }
+	if (total >> 62)
+		return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac_host: unexpected shared-memory window layout");
 	*n_hits = (int64_t)total;
 	int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 	btbb_b200_hit *res = NULL;

@@ -31,6 +31,8 @@ struct btbb_b200_ctx {
 	uint32_t *d_map2;            /* bulk kernel: 2^19-bit map of reachable low-32 syndromes, both tails (k <= 2) */
 	uint64_t cc[2];              /* 34-bit syndrome of PN ^ (legal tail << 57) */
 	uint32_t m32, m33;           /* parity masks over codeword bits 32..56 for syndrome bits 32 / 33 */
+	void *d_xp;                  /* ring of 16 x 128-byte exact-test parameter blocks (bulk kernel) */
+	unsigned xp_next;
 	bt_err_slot *d_err;          /* hash table, capacity 1 << err_log2 (NULL when table_k == 0) */
 	int err_log2;
 	long err_entries;

@@ -452,16 +452,18 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	a.nstrips = nstrips;
 	a.lut = ctx->d_lut2;
 	a.map = ctx->d_map2;
-	a.cc[0] = ctx->cc[0]; a.cc[1] = ctx->cc[1];
-	a.m32 = ctx->m32; a.m33 = ctx->m33;
-	memset(&a.common, 0, sizeof(a.common));
-	a.common.bias = bias;
-	a.common.kmax = k;
-	a.common.err = ctx->d_err;
-	a.common.err_log2 = ctx->err_log2;
-	a.common.hits = d_out;
-	a.common.max_hits = max_hits;
-	a.common.count = d_count;
+	v3::xparams xp;
+	memset(&xp, 0, sizeof(xp));
+	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
+	xp.m32 = ctx->m32; xp.m33 = ctx->m33;
+	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err;
+	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
+	if (!ctx->d_xp)
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_xp, 16 * 128));
+	static_assert(sizeof(v3::xparams) <= 128, "xparams slot");
+	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
+	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
+	a.xp = (const v3::xparams *)slot;
 	static bool attr_set[16];
 	if (ctx->device < 16 && !attr_set[ctx->device]) {
 		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
@@ -561,6 +563,8 @@ extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream
 	unsigned long long total = 0;
 	BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
+	if (total >> 62)
+		return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
 	*n_hits = (int64_t)total;
 	int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 	btbb_b200_hit *res = NULL;
