@@ -368,6 +368,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 }
 
 #include "scan_v3.cuh"
+#include "scan_v4.cuh"
 
 }  // namespace
 
@@ -428,7 +429,7 @@ static int scan_launch_v1(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n
 
 /*
  * Dispatcher.  The promiscuous scan with tables for k <= 2 runs the warp-autonomous bulk
- * kernel (scan_v3.cuh) over every whole 4096-symbol strip that starts on a 32-byte
+ * kernel (scan_v4.cuh; BTBB_B200_SCAN=v3 selects its predecessor) over every whole 4096-symbol strip that starts on a 32-byte
  * boundary; the unaligned head and the ragged tail go through the tile kernel above, as
  * do known-LAP scans and the larger error tables.  BTBB_B200_SCAN=v1 forces the tile kernel.
  */
@@ -446,12 +447,6 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	if (nstrips < 1)
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	const int64_t body_end = head + nstrips * v3::STRIP;
-	v3::args a;
-	a.base = d_stream + head;
-	a.pos0 = head;
-	a.nstrips = nstrips;
-	a.lut = ctx->d_lut2;
-	a.map = ctx->d_map2;
 	v3::xparams xp;
 	memset(&xp, 0, sizeof(xp));
 	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
@@ -463,16 +458,26 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	static_assert(sizeof(v3::xparams) <= 128, "xparams slot");
 	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
 	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
-	a.xp = (const v3::xparams *)slot;
 	static bool attr_set[16];
 	if (ctx->device < 16 && !attr_set[ctx->device]) {
 		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
+		BT_CUDA_TRY(cudaFuncSetAttribute(v4::scan_promisc_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v4::SMEM_BYTES));
 		attr_set[ctx->device] = true;
 	}
 	int64_t grid = ctx->sm_count;
 	const int64_t need = (nstrips + v3::WARPS - 1) / v3::WARPS;
 	if (grid > need) grid = need;
-	v3::scan_promisc_v3<<<(unsigned)grid, v3::WARPS * 32, v3::SMEM_BYTES, st>>>(a);
+	if (env && !strcmp(env, "v3")) {
+		v3::args a;
+		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
+		a.lut = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
+		v3::scan_promisc_v3<<<(unsigned)grid, v3::WARPS * 32, v3::SMEM_BYTES, st>>>(a);
+	} else {
+		v4::args a;
+		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
+		a.lut = ctx->d_lut4; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
+		v4::scan_promisc_v4<<<(unsigned)grid, v4::WARPS * 32, v4::SMEM_BYTES, st>>>(a);
+	}
 	BT_CUDA_TRY(cudaGetLastError());
 	int rc = BTBB_B200_OK;
 	if (head > 0)

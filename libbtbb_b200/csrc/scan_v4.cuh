@@ -1,0 +1,271 @@
+/*
+ * scan_v4.cuh -- the bulk promiscuous access-code scan, second generation.
+ *
+ * Same decision per window as promiscuous_packet_search (bluetooth_packet.c:368-420) and the
+ * same load / pack / bit-sliced Barker filter as scan_v3.cuh.  What changed is how the ~1/8
+ * surviving positions are tested, because v3 was bound by shared-memory wavefronts (80 % of
+ * peak at 46 % of the HBM roofline):
+ *
+ *   - each lane tests the first five candidates of each of its words IN PLACE, from the
+ *     window words it already holds in registers (no queue write, no queue read, no
+ *     re-fetch of the window): that covers ~93 % of all candidates;
+ *   - the low 32 syndrome bits come from four LANE-PRIVATE tables over codeword bits
+ *     32..38 / 39..44 / 45..50 / 51..56 (gen_syndrome, :147-159, regrouped): entry e of lane
+ *     L lives in bank L, so every lookup is a single conflict-free wavefront;
+ *   - only the candidates beyond the fifth of a word (and nothing else) go through the
+ *     row-major queue + all-lanes-busy consumer of v3;
+ *   - a row with more than 255 candidates (never on real captures, only on adversarial
+ *     input) is simply looped in place until every lane is done.
+ *
+ * Shared memory, by absolute shared-window address: exact queues from 0x800, the four tables
+ * at 0x4000/0x8000/0xA000/0xC000 (128+64+64+64 entries x 32 lanes x 4 B), the 2^19-bit
+ * syndrome map at 0x10000, per-warp bit tile + overflow queue from 0x20000.
+ */
+#pragma once
+
+namespace v4 {
+
+using v3::ld256;
+using v3::lds32;
+using v3::lds32o;
+using v3::lds16o;
+using v3::sts32;
+using v3::sts16o;
+using v3::pack32;
+using v3::bfind;
+using v3::barker_mask;
+using v3::xparams;
+
+constexpr int WARPS = 32;
+constexpr int K = 4;
+constexpr int SW = 32 * K;
+constexpr int STRIP = SW * 32;
+constexpr int BLOG = 19;
+constexpr int MAP_WORDS = 1 << (BLOG - 5);
+constexpr int INLINE_SLOTS = 5;
+constexpr int QCAP = 1024;
+constexpr int XCAP = 20;
+constexpr int LUT_ENTRIES = 128 + 64 + 64 + 64;    /* fields of 7, 6, 6, 6 bits */
+constexpr uint32_t SA_X = 0x0800, X_BYTES = 96 * 4;
+constexpr uint32_t SA_T0 = 0x4000, SA_T1 = 0x8000, SA_T2 = 0xA000, SA_T3 = 0xC000;
+constexpr uint32_t SA_MAP = 0x10000, SA_WARP = 0x20000;
+constexpr uint32_t S_BYTES = (SW + 8) * 4;
+constexpr uint32_t WARP_BYTES = S_BYTES + QCAP * 2;
+constexpr uint32_t SA_END = SA_WARP + WARPS * WARP_BYTES;
+constexpr size_t SMEM_BYTES = SA_END;
+
+struct args {
+	const uint8_t *base;     /* 32-byte aligned; base[0] is stream position pos0 */
+	int64_t pos0;
+	int64_t nstrips;
+	const uint32_t *lut;     /* LUT_ENTRIES words: the four field tables back to back */
+	const uint32_t *map;     /* MAP_WORDS */
+	const xparams *xp;
+};
+
+/* low 32 syndrome bits of the received part (bits 0..56): four conflict-free lookups.
+ * lane4 = 4 * lane; a table entry e of this lane sits at base + 128 e + 4 lane. */
+__device__ __forceinline__ uint32_t syn_lo32(uint32_t lo, uint32_t hi, uint32_t lane4)
+{
+	const uint32_t t0 = lds32o<SA_T0>(((hi << 7) & (127u << 7)) | lane4);
+	const uint32_t t1 = lds32o<SA_T1>((hi & (63u << 7)) | lane4);
+	const uint32_t t2 = lds32o<SA_T2>(((hi >> 6) & (63u << 7)) | lane4);
+	const uint32_t t3 = lds32o<SA_T3>(((hi >> 12) & (63u << 7)) | lane4);
+	return lo ^ t0 ^ t1 ^ t2 ^ t3;
+}
+
+__device__ __forceinline__ uint32_t map_bit(uint32_t sy)
+{
+	const uint32_t mw = lds32o<SA_MAP>((sy >> (32 - BLOG + 5 - 2)) & (uint32_t)((MAP_WORDS - 1) * 4));
+	return (mw >> (sy & 31)) & 1;
+}
+
+/* exact test needs the 2-LUT-free syndrome too: reuse the lane-private tables */
+__device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo, uint32_t hi)
+{
+	const uint32_t lane4 = (threadIdx.x & 31) * 4;
+	const uint32_t tail = hi >> 25;
+	const int cls = __popc((tail ^ BT_BARKER_A) & 0x7f) <= 3 ? 0 : 1;
+	uint64_t syn = (uint64_t)syn_lo32(lo, hi, lane4) | ((uint64_t)(__popc(hi & xp->m32) & 1) << 32) |
+		       ((uint64_t)(__popc(hi & xp->m33) & 1) << 33);
+	syn ^= xp->cc[cls];
+	uint64_t sw = (((uint64_t)hi << 32) | lo) & 0x01ffffffffffffffULL;
+	sw |= (uint64_t)(cls ? BT_BARKER_B : BT_BARKER_A) << 57;
+	uint32_t e = 0;
+	if (syn) {
+		e = 0xff;
+		const bt_err_slot *tab = xp->err;
+		if (tab) {
+			const int lg = xp->err_log2;
+			const uint64_t mask = ((uint64_t)1 << lg) - 1;
+			uint64_t h = bt_err_hash(syn, lg);
+			for (;;) {
+				const bt_err_slot sl = tab[h];
+				if (sl.syn == syn) { sw ^= sl.err; e = (uint32_t)__popcll(sl.err); break; }
+				if (sl.syn == 0) break;
+				h = (h + 1) & mask;
+			}
+		}
+	}
+	if ((int)e > xp->kmax) return;
+	const uint32_t lap = (uint32_t)(sw >> 34) & 0xffffffu;
+	const int64_t max_hits = xp->max_hits;
+	if (max_hits < 0) {          /* first-hit mode, see push_hit() */
+		atomicMin(xp->count, ((unsigned long long)(pos + xp->bias) << 32) | ((unsigned long long)lap << 8) | e);
+		return;
+	}
+	const unsigned long long slot = atomicAdd(xp->count, 1ULL);
+	if ((int64_t)slot < max_hits) {
+		btbb_b200_hit h;
+		h.offset = pos + xp->bias; h.lap = lap; h.ac_errors = (uint8_t)e; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+		xp->hits[slot] = h;
+	}
+}
+
+__device__ __noinline__ void flush4(const xparams *xp, uint32_t x_sa, int lane)
+{
+	__syncwarp();
+	uint32_t n = lds32(x_sa);
+	if (n > XCAP) n = XCAP;
+	if ((uint32_t)lane < n) {
+		const uint32_t xa = x_sa + 4 + 16 * lane;
+		const uint32_t p0 = lds32o<0>(xa), p1 = lds32o<4>(xa), lo = lds32o<8>(xa), hi = lds32o<12>(xa);
+		exact4(xp, (int64_t)(((uint64_t)p1 << 32) | p0), lo, hi);
+	}
+	__syncwarp();
+	if (lane == 0) sts32(x_sa, 0);
+	__syncwarp();
+}
+
+__device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, int64_t pos, uint32_t lo, uint32_t hi)
+{
+	uint32_t slot;
+	asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(x_sa) : "memory");
+	if (slot < XCAP) {
+		const uint32_t xa = x_sa + 4 + 16 * slot;
+		sts32(xa, (uint32_t)pos); sts32(xa + 4, (uint32_t)(pos >> 32)); sts32(xa + 8, lo); sts32(xa + 12, hi);
+	} else
+		exact4(xp, pos, lo, hi);
+}
+
+/* take the highest remaining candidate of this lane's word (if any) and test it in place */
+__device__ __forceinline__ void slot(uint32_t &c, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t lane4,
+				     const xparams *xp, uint32_t x_sa, int64_t word_pos)
+{
+	if (c) {
+		const uint32_t q = bfind(c);
+		c ^= 1u << q;
+		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
+		if (map_bit(syn_lo32(lo, hi, lane4)))
+			park4(xp, x_sa, word_pos + q, lo, hi);
+	}
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(smem);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const xparams *xp = a.xp;
+	if (smem_sa > SA_X) { if (threadIdx.x == 0) atomicAdd(xp->count, 1ULL << 62); return; }  /* never: layout assumption */
+
+	/* lane-private copies of the four field tables: entry e -> base + 128 e + 4 lane */
+	for (int i = threadIdx.x; i < LUT_ENTRIES * 32; i += WARPS * 32) {
+		const int e = i >> 5, l = i & 31;
+		const uint32_t base = e < 128 ? SA_T0 + 128 * e : e < 192 ? SA_T1 + 128 * (e - 128)
+				    : e < 256 ? SA_T2 + 128 * (e - 192) : SA_T3 + 128 * (e - 256);
+		sts32(base + 4 * l, a.lut[e]);
+	}
+	for (int i = threadIdx.x; i < MAP_WORDS; i += WARPS * 32) sts32(SA_MAP + 4 * i, a.map[i]);
+	const uint32_t x_sa = SA_X + wid * X_BYTES;
+	const uint32_t s_sa = SA_WARP + wid * WARP_BYTES;
+	const uint32_t q_sa = s_sa + S_BYTES;
+	if (lane == 0) sts32(x_sa, 0);
+	__syncthreads();
+
+	const int64_t gw = (int64_t)blockIdx.x * WARPS + wid, nw = (int64_t)gridDim.x * WARPS;
+	const int64_t s_begin = a.nstrips * gw / nw, s_end = a.nstrips * (gw + 1) / nw;
+	const uint32_t lane4 = 4 * lane, my_sa = s_sa + lane4;
+
+	for (int64_t s = s_begin; s < s_end; s++) {
+		uint32_t wv[K];
+		/* ---- load + pack ---- */
+		{
+			uint32_t raw[K][8];
+			const uint8_t *p = a.base + s * STRIP + lane * 32;
+			#pragma unroll
+			for (int k = 0; k < K; k++) ld256(p + k * 1024, raw[k]);
+			#pragma unroll
+			for (int k = 0; k < K; k++) { wv[k] = pack32(raw[k]); sts32(my_sa + 128 * k, wv[k]); }
+			if (lane < 2) {        /* 64-symbol halo = first two words of the next strip */
+				ld256(p + STRIP, raw[0]);
+				sts32(my_sa + 128 * K, pack32(raw[0]));
+			}
+			if (s + 1 < s_end) {
+				#pragma unroll
+				for (int k = 0; k < K; k++)
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(p + STRIP + k * 1024));
+			}
+		}
+		__syncwarp();
+		const int64_t strip_pos = a.pos0 + s * STRIP;
+		/* ---- per row: filter, then the first candidates of every word in place ---- */
+		uint32_t rem[K];
+		#pragma unroll
+		for (int k = 0; k < K; k++) {
+			const uint32_t w1 = lds32(my_sa + 128 * k + 4), w2 = lds32(my_sa + 128 * k + 8);
+			uint32_t c = barker_mask(w1, w2);
+			const int64_t word_pos = strip_pos + (k * 32 + lane) * 32;
+			const uint32_t row_total = __reduce_add_sync(0xffffffffu, __popc(c));
+			if (row_total <= 255) {
+				#pragma unroll
+				for (int t = 0; t < INLINE_SLOTS; t++)
+					slot(c, wv[k], w1, w2, lane4, xp, x_sa, word_pos);
+			} else {
+				while (__any_sync(0xffffffffu, c != 0))
+					slot(c, wv[k], w1, w2, lane4, xp, x_sa, word_pos);
+			}
+			rem[k] = c;
+		}
+		/* ---- the few candidates beyond the inline slots: row-major queue, all lanes busy ---- */
+		const uint32_t cnt = __popc(rem[0]) | (__popc(rem[1]) << 8) | (__popc(rem[2]) << 16) | (__popc(rem[3]) << 24);
+		uint32_t inc = cnt;                  /* four 8-bit inclusive scans; a row total never exceeds 255 here */
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += u;
+		}
+		const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+		if (tot) {
+			const uint32_t ex = inc - cnt;
+			uint32_t nq = 0;
+			#pragma unroll
+			for (int k = 0; k < K; k++) {
+				uint32_t m = rem[k];
+				uint32_t dst = q_sa + 2 * (nq + ((ex >> (8 * k)) & 0xff));
+				const uint32_t ebase = (uint32_t)(k * 32 + lane) << 7;
+				while (m) {
+					const uint32_t q0 = bfind(m);
+					m ^= 1u << q0;
+					sts16o<0>(dst, ebase | q0);
+					dst += 2;
+				}
+				nq += (tot >> (8 * k)) & 0xff;
+			}
+			__syncwarp();
+			for (uint32_t i = lane; i < nq; i += 32) {
+				const uint32_t e = lds16o<0>(q_sa + 2 * i);
+				const uint32_t wa = s_sa + (e >> 5);
+				const uint32_t w0 = lds32o<0>(wa), w1 = lds32o<4>(wa), w2 = lds32o<8>(wa);
+				const uint32_t lo = __funnelshift_r(w0, w1, e), hi = __funnelshift_r(w1, w2, e);
+				if (map_bit(syn_lo32(lo, hi, lane4)))
+					park4(xp, x_sa, strip_pos + (e >> 7) * 32 + (e & 31), lo, hi);
+			}
+		}
+		__syncwarp();
+		if (lds32(x_sa) >= XCAP / 2) flush4(xp, x_sa, lane);
+	}
+	flush4(xp, x_sa, lane);
+}
+
+}  // namespace v4

@@ -73,7 +73,7 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	 * bits, bit = low 5) of every value that part can take for an acceptable window: the
 	 * table syndromes (and zero) XOR the constant of either legal tail.  Only built while the
 	 * map stays sparse (k <= 2: at most 3424 of 2^19 bits set). --- */
-	ctx->d_lut2 = NULL; ctx->d_map2 = NULL;
+	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL;
 	ctx->cc[0] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_A << 57));
 	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
 	ctx->m32 = ctx->m33 = 0;
@@ -94,6 +94,17 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 			for (int j = 0; j < bbits; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + abits + j];
 			lut[((size_t)1 << abits) + v] = (uint32_t)sy;
 		}
+		/* v4: the same 25 bits as four lane-replicated field tables (7, 6, 6, 6 bits) */
+		std::vector<uint32_t> lut4;
+		const int fw[4] = {7, 6, 6, 6};
+		for (int f = 0, pos = 0; f < 4; pos += fw[f], f++)
+			for (uint32_t v = 0; v < (1u << fw[f]); v++) {
+				uint64_t sy = 0;
+				for (int j = 0; j < fw[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + pos + j];
+				lut4.push_back((uint32_t)sy);
+			}
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_lut4, lut4.size() * sizeof(uint32_t)));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut4, lut4.data(), lut4.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		std::vector<uint32_t> map((size_t)1 << (19 - 5), 0u);
 		auto map_add = [&](uint32_t s32) {
 			for (int c = 0; c < 2; c++) {
@@ -135,6 +146,7 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_err) cudaFree(ctx->d_err);
 	if (ctx->d_lut2) cudaFree(ctx->d_lut2);
 	if (ctx->d_map2) cudaFree(ctx->d_map2);
+	if (ctx->d_lut4) cudaFree(ctx->d_lut4);
 	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
-	ctx->d_lut2 = NULL; ctx->d_map2 = NULL;
+	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL;
 }
