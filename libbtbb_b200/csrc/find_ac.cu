@@ -458,12 +458,6 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	static_assert(sizeof(v3::xparams) <= 128, "xparams slot");
 	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
 	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
-	static bool attr_set[16];
-	if (ctx->device < 16 && !attr_set[ctx->device]) {
-		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
-		BT_CUDA_TRY(cudaFuncSetAttribute(v4::scan_promisc_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v4::SMEM_BYTES));
-		attr_set[ctx->device] = true;
-	}
 	int64_t grid = ctx->sm_count;
 	const int64_t need = (nstrips + v3::WARPS - 1) / v3::WARPS;
 	if (grid > need) grid = need;
@@ -471,12 +465,22 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 		v3::args a;
 		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
 		a.lut = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
+		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
 		v3::scan_promisc_v3<<<(unsigned)grid, v3::WARPS * 32, v3::SMEM_BYTES, st>>>(a);
 	} else {
 		v4::args a;
 		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
-		a.lut = ctx->d_lut4; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
-		v4::scan_promisc_v4<<<(unsigned)grid, v4::WARPS * 32, v4::SMEM_BYTES, st>>>(a);
+		a.lut = ctx->d_lut4; a.lut2 = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
+		/* experiment switch (developer): v4a..v4f pick LUT mode / inline slots / branch-free slots */
+		void (*kern)(const v4::args) = v4::scan_promisc_v4<1, 5, true>;
+		if (env && !strcmp(env, "v4a")) kern = v4::scan_promisc_v4<0, 5, false>;
+		else if (env && !strcmp(env, "v4b")) kern = v4::scan_promisc_v4<1, 5, true>;
+		else if (env && !strcmp(env, "v4c")) kern = v4::scan_promisc_v4<1, 4, true>;
+		else if (env && !strcmp(env, "v4d")) kern = v4::scan_promisc_v4<0, 5, true>;
+		else if (env && !strcmp(env, "v4e")) kern = v4::scan_promisc_v4<1, 6, true>;
+		else if (env && !strcmp(env, "v4f")) kern = v4::scan_promisc_v4<1, 5, false>;
+		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v4::SMEM_BYTES));
+		kern<<<(unsigned)grid, v4::WARPS * 32, v4::SMEM_BYTES, st>>>(a);
 	}
 	BT_CUDA_TRY(cudaGetLastError());
 	int rc = BTBB_B200_OK;

@@ -58,7 +58,8 @@ struct args {
 	const uint8_t *base;     /* 32-byte aligned; base[0] is stream position pos0 */
 	int64_t pos0;
 	int64_t nstrips;
-	const uint32_t *lut;     /* LUT_ENTRIES words: the four field tables back to back */
+	const uint32_t *lut;     /* LUT_ENTRIES words: the four field tables back to back (LUTMODE 0) */
+	const uint32_t *lut2;    /* v3 layout: LUT A (2^13) then LUT B (2^12) (LUTMODE 1) */
 	const uint32_t *map;     /* MAP_WORDS */
 	const xparams *xp;
 };
@@ -74,6 +75,20 @@ __device__ __forceinline__ uint32_t syn_lo32(uint32_t lo, uint32_t hi, uint32_t 
 	return lo ^ t0 ^ t1 ^ t2 ^ t3;
 }
 
+/* LUTMODE 1: two shared tables over bits 32..44 / 45..56 (half the instructions, but the
+ * lookups collide in the banks like any random access) */
+__device__ __forceinline__ uint32_t syn_lo32_2(uint32_t lo, uint32_t hi)
+{
+	const uint32_t ta = lds32o<0x8000>((hi << 2) & (8191u << 2));
+	const uint32_t tb = lds32o<0x4000>((hi >> 11) & (4095u << 2));
+	return lo ^ ta ^ tb;
+}
+template <int LUTMODE>
+__device__ __forceinline__ uint32_t syn32(uint32_t lo, uint32_t hi, uint32_t lane4)
+{
+	return LUTMODE ? syn_lo32_2(lo, hi) : syn_lo32(lo, hi, lane4);
+}
+
 __device__ __forceinline__ uint32_t map_bit(uint32_t sy)
 {
 	const uint32_t mw = lds32o<SA_MAP>((sy >> (32 - BLOG + 5 - 2)) & (uint32_t)((MAP_WORDS - 1) * 4));
@@ -81,12 +96,13 @@ __device__ __forceinline__ uint32_t map_bit(uint32_t sy)
 }
 
 /* exact test needs the 2-LUT-free syndrome too: reuse the lane-private tables */
+template <int LUTMODE>
 __device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo, uint32_t hi)
 {
 	const uint32_t lane4 = (threadIdx.x & 31) * 4;
 	const uint32_t tail = hi >> 25;
 	const int cls = __popc((tail ^ BT_BARKER_A) & 0x7f) <= 3 ? 0 : 1;
-	uint64_t syn = (uint64_t)syn_lo32(lo, hi, lane4) | ((uint64_t)(__popc(hi & xp->m32) & 1) << 32) |
+	uint64_t syn = (uint64_t)syn32<LUTMODE>(lo, hi, lane4) | ((uint64_t)(__popc(hi & xp->m32) & 1) << 32) |
 		       ((uint64_t)(__popc(hi & xp->m33) & 1) << 33);
 	syn ^= xp->cc[cls];
 	uint64_t sw = (((uint64_t)hi << 32) | lo) & 0x01ffffffffffffffULL;
@@ -122,6 +138,7 @@ __device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo,
 	}
 }
 
+template <int LUTMODE>
 __device__ __noinline__ void flush4(const xparams *xp, uint32_t x_sa, int lane)
 {
 	__syncwarp();
@@ -130,13 +147,14 @@ __device__ __noinline__ void flush4(const xparams *xp, uint32_t x_sa, int lane)
 	if ((uint32_t)lane < n) {
 		const uint32_t xa = x_sa + 4 + 16 * lane;
 		const uint32_t p0 = lds32o<0>(xa), p1 = lds32o<4>(xa), lo = lds32o<8>(xa), hi = lds32o<12>(xa);
-		exact4(xp, (int64_t)(((uint64_t)p1 << 32) | p0), lo, hi);
+		exact4<LUTMODE>(xp, (int64_t)(((uint64_t)p1 << 32) | p0), lo, hi);
 	}
 	__syncwarp();
 	if (lane == 0) sts32(x_sa, 0);
 	__syncwarp();
 }
 
+template <int LUTMODE>
 __device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, int64_t pos, uint32_t lo, uint32_t hi)
 {
 	uint32_t slot;
@@ -145,22 +163,34 @@ __device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, int64_t pos
 		const uint32_t xa = x_sa + 4 + 16 * slot;
 		sts32(xa, (uint32_t)pos); sts32(xa + 4, (uint32_t)(pos >> 32)); sts32(xa + 8, lo); sts32(xa + 12, hi);
 	} else
-		exact4(xp, pos, lo, hi);
+		exact4<LUTMODE>(xp, pos, lo, hi);
 }
 
-/* take the highest remaining candidate of this lane's word (if any) and test it in place */
+/* take the highest remaining candidate of this lane's word (if any) and test it in place.
+ * BF (branch-free): lanes without a candidate run the same instructions on a dummy window
+ * (bfind(0) = -1, the shift below clamps to 0) and are masked out of the final decision. */
+template <int LUTMODE, bool BF>
 __device__ __forceinline__ void slot(uint32_t &c, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t lane4,
 				     const xparams *xp, uint32_t x_sa, int64_t word_pos)
 {
-	if (c) {
+	if (BF) {
+		const uint32_t q = bfind(c);
+		uint32_t bit;
+		asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(q));
+		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
+		if (map_bit(syn32<LUTMODE>(lo, hi, lane4)) && bit)
+			park4<LUTMODE>(xp, x_sa, word_pos + q, lo, hi);
+		c ^= bit;
+	} else if (c) {
 		const uint32_t q = bfind(c);
 		c ^= 1u << q;
 		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
-		if (map_bit(syn_lo32(lo, hi, lane4)))
-			park4(xp, x_sa, word_pos + q, lo, hi);
+		if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
+			park4<LUTMODE>(xp, x_sa, word_pos + q, lo, hi);
 	}
 }
 
+template <int LUTMODE, int NSLOTS, bool BF>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -169,18 +199,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 	const xparams *xp = a.xp;
 	if (smem_sa > SA_X) { if (threadIdx.x == 0) atomicAdd(xp->count, 1ULL << 62); return; }  /* never: layout assumption */
 
-	/* lane-private copies of the four field tables: entry e -> base + 128 e + 4 lane */
-	for (int i = threadIdx.x; i < LUT_ENTRIES * 32; i += WARPS * 32) {
-		const int e = i >> 5, l = i & 31;
-		const uint32_t base = e < 128 ? SA_T0 + 128 * e : e < 192 ? SA_T1 + 128 * (e - 128)
-				    : e < 256 ? SA_T2 + 128 * (e - 192) : SA_T3 + 128 * (e - 256);
-		sts32(base + 4 * l, a.lut[e]);
+	if (LUTMODE == 0) {
+		/* lane-private copies of the four field tables: entry e -> base + 128 e + 4 lane */
+		for (int i = threadIdx.x; i < LUT_ENTRIES * 32; i += WARPS * 32) {
+			const int e = i >> 5, l = i & 31;
+			const uint32_t base = e < 128 ? SA_T0 + 128 * e : e < 192 ? SA_T1 + 128 * (e - 128)
+					    : e < 256 ? SA_T2 + 128 * (e - 192) : SA_T3 + 128 * (e - 256);
+			sts32(base + 4 * l, a.lut[e]);
+		}
+	} else {
+		for (int i = threadIdx.x; i < 8192; i += WARPS * 32) sts32(0x8000 + 4 * i, a.lut2[i]);
+		for (int i = threadIdx.x; i < 4096; i += WARPS * 32) sts32(0x4000 + 4 * i, a.lut2[8192 + i]);
 	}
 	for (int i = threadIdx.x; i < MAP_WORDS; i += WARPS * 32) sts32(SA_MAP + 4 * i, a.map[i]);
 	const uint32_t x_sa = SA_X + wid * X_BYTES;
 	const uint32_t s_sa = SA_WARP + wid * WARP_BYTES;
 	const uint32_t q_sa = s_sa + S_BYTES;
-	if (lane == 0) sts32(x_sa, 0);
+	const uint32_t qn_sa = x_sa + 95 * 4;                   /* overflow-queue fill level */
+	if (lane == 0) { sts32(x_sa, 0); sts32(qn_sa, 0); }
 	__syncthreads();
 
 	const int64_t gw = (int64_t)blockIdx.x * WARPS + wid, nw = (int64_t)gridDim.x * WARPS;
@@ -209,63 +245,70 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		}
 		__syncwarp();
 		const int64_t strip_pos = a.pos0 + s * STRIP;
-		/* ---- per row: filter, then the first candidates of every word in place ---- */
-		uint32_t rem[K];
+		/* ---- filter all rows, then the first candidates of every word in place; the rows
+		 * are independent dependency chains, so slot t of all four rows is issued together ---- */
+		uint32_t rem[K], w1[K], w2[K];
 		#pragma unroll
 		for (int k = 0; k < K; k++) {
-			const uint32_t w1 = lds32(my_sa + 128 * k + 4), w2 = lds32(my_sa + 128 * k + 8);
-			uint32_t c = barker_mask(w1, w2);
-			const int64_t word_pos = strip_pos + (k * 32 + lane) * 32;
-			const uint32_t row_total = __reduce_add_sync(0xffffffffu, __popc(c));
-			if (row_total <= 255) {
+			w1[k] = lds32(my_sa + 128 * k + 4); w2[k] = lds32(my_sa + 128 * k + 8);
+			rem[k] = barker_mask(w1[k], w2[k]);
+		}
+		const uint32_t t01 = __reduce_add_sync(0xffffffffu, __popc(rem[0]) | (__popc(rem[1]) << 16));
+		const uint32_t t23 = __reduce_add_sync(0xffffffffu, __popc(rem[2]) | (__popc(rem[3]) << 16));
+		const int64_t lane_pos = strip_pos + lane * 32;
+		if (((t01 | t23) & 0xff00ff00u) == 0) {          /* every row holds <= 255 candidates */
+			#pragma unroll
+			for (int t = 0; t < NSLOTS; t++) {
 				#pragma unroll
-				for (int t = 0; t < INLINE_SLOTS; t++)
-					slot(c, wv[k], w1, w2, lane4, xp, x_sa, word_pos);
-			} else {
-				while (__any_sync(0xffffffffu, c != 0))
-					slot(c, wv[k], w1, w2, lane4, xp, x_sa, word_pos);
+				for (int k = 0; k < K; k++)
+					slot<LUTMODE, BF>(rem[k], wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
 			}
-			rem[k] = c;
+		} else {
+			#pragma unroll
+			for (int k = 0; k < K; k++) {
+				uint32_t c = rem[k];
+				while (__any_sync(0xffffffffu, c != 0))
+					slot<LUTMODE, false>(c, wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
+				rem[k] = 0;
+			}
 		}
-		/* ---- the few candidates beyond the inline slots: row-major queue, all lanes busy ---- */
-		const uint32_t cnt = __popc(rem[0]) | (__popc(rem[1]) << 8) | (__popc(rem[2]) << 16) | (__popc(rem[3]) << 24);
-		uint32_t inc = cnt;                  /* four 8-bit inclusive scans; a row total never exceeds 255 here */
-		#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-			if (lane >= d) inc += u;
-		}
-		const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-		if (tot) {
-			const uint32_t ex = inc - cnt;
-			uint32_t nq = 0;
+		/* ---- the few candidates beyond the inline slots: queue + all-lanes-busy consumer.
+		 * A lane reserves its entries with one shared-memory atomic (a row holds at most 255
+		 * candidates here, so the queue cannot overflow). ---- */
+		if (__any_sync(0xffffffffu, (rem[0] | rem[1] | rem[2] | rem[3]) != 0)) {
 			#pragma unroll
 			for (int k = 0; k < K; k++) {
 				uint32_t m = rem[k];
-				uint32_t dst = q_sa + 2 * (nq + ((ex >> (8 * k)) & 0xff));
-				const uint32_t ebase = (uint32_t)(k * 32 + lane) << 7;
-				while (m) {
-					const uint32_t q0 = bfind(m);
-					m ^= 1u << q0;
-					sts16o<0>(dst, ebase | q0);
-					dst += 2;
+				if (m) {
+					uint32_t at;
+					asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(at) : "r"(qn_sa), "r"(__popc(m)) : "memory");
+					uint32_t dst = q_sa + 2 * at;
+					const uint32_t ebase = (uint32_t)(k * 32 + lane) << 7;
+					do {
+						const uint32_t q0 = bfind(m);
+						m ^= 1u << q0;
+						sts16o<0>(dst, ebase | q0);
+						dst += 2;
+					} while (m);
 				}
-				nq += (tot >> (8 * k)) & 0xff;
 			}
 			__syncwarp();
+			const uint32_t nq = lds32(qn_sa);
 			for (uint32_t i = lane; i < nq; i += 32) {
 				const uint32_t e = lds16o<0>(q_sa + 2 * i);
 				const uint32_t wa = s_sa + (e >> 5);
 				const uint32_t w0 = lds32o<0>(wa), w1 = lds32o<4>(wa), w2 = lds32o<8>(wa);
 				const uint32_t lo = __funnelshift_r(w0, w1, e), hi = __funnelshift_r(w1, w2, e);
-				if (map_bit(syn_lo32(lo, hi, lane4)))
-					park4(xp, x_sa, strip_pos + (e >> 7) * 32 + (e & 31), lo, hi);
+				if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
+					park4<LUTMODE>(xp, x_sa, strip_pos + (e >> 7) * 32 + (e & 31), lo, hi);
 			}
+			__syncwarp();
+			if (lane == 0) sts32(qn_sa, 0);
 		}
 		__syncwarp();
-		if (lds32(x_sa) >= XCAP / 2) flush4(xp, x_sa, lane);
+		if (lds32(x_sa) >= XCAP / 2) flush4<LUTMODE>(xp, x_sa, lane);
 	}
-	flush4(xp, x_sa, lane);
+	flush4<LUTMODE>(xp, x_sa, lane);
 }
 
 }  // namespace v4

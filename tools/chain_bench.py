@@ -1,0 +1,74 @@
+"""BASELINE configs[2]: full chain on a 79-channel interleaved capture.
+
+    python tools/chain_bench.py [--blocks N] > profiles/r01_chain.json
+
+Capture layout [block][79 channels][4096 symbols] (SURVEY.md 8d cfg 3): every 4096-symbol
+channel block carries one planted packet (DM1 / DM3 / DH1 / FHS).  Chain: find_ac (promiscuous,
+k=2) -> per hit the 64-clock try_clock + crc_check sweep (the inner loop of
+bluetooth_piconet.c:675-689) and the known-clock btbb_decode_header + btbb_decode_payload.
+Everything stays on the device; a sample is checked against the oracle."""
+import argparse, ctypes as C, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import util
+from util import B
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--blocks", type=int, default=2000)
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+lib = B.lib()
+BLK, CH = 4096, 79
+n = a.blocks * CH * BLK
+cfg = B.synth_cfg(n + 63, stride=BLK, ber=0.001, mix=("DM1", "DM3", "DH1", "FHS"))
+d = torch.empty(n + 63, dtype=torch.uint8, device="cuda")
+B.check(lib.btbb_b200_synth_dev(C.byref(cfg), d.data_ptr(), 0)); torch.cuda.synchronize()
+cap = a.blocks * CH * 2 + 4096
+d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+ctx = B.Context(0, 2)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def chain(mode):
+    cnt, rc = ctx.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, k=2, stream=st)
+    off = d_hits[:cnt].view(torch.int64)[:, 0]
+    pk = torch.zeros((cnt, 24), dtype=torch.uint8, device="cuda")
+    pk.view(torch.int64)[:, 0] = off
+    length = torch.clamp((off // BLK + 1) * BLK - off, max=3125).to(torch.int32)   # symbols left in the channel block
+    pk.view(torch.int32)[:, 2] = length
+    pk[:, 17] = 1                                                                  # whitened
+    out = torch.empty((cnt * (64 if mode == 1 else 1), 372), dtype=torch.uint8, device="cuda")
+    B.check(lib.btbb_b200_decode_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, mode, out.data_ptr(), st))
+    return cnt, pk, out
+
+
+res = {"workload": f"{a.blocks} blocks x 79 channels x 4096 symbols, one packet per channel block, BER 0.1%",
+       "symbols": n}
+for mode, name in ((1, "find_ac + 64-clock try_clock/crc_check sweep"), (0, "find_ac + decode (clock 0, UAP 0: header reject path)")):
+    for _ in range(2):
+        cnt, pk, out = chain(mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.iters):
+        cnt, pk, out = chain(mode)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.iters
+    res[name] = {"ms": ms, "packets": int(cnt), "packets_per_s": cnt / (ms / 1e3), "gbit_s": n / (ms / 1e3) / 1e9}
+# parity sample: first 300 hits, 64 clocks each, against the oracle
+cnt, pk, out = chain(1)
+torch.cuda.synchronize()
+O = util.oracle()
+s = d[: 400 * BLK + 4000].cpu().numpy()
+pkh = pk[:300].cpu().numpy().reshape(-1).view(B.PKTIN_DTYPE)
+got = out[: 300 * 64].cpu().numpy().reshape(-1).view(B.DECODED_DTYPE)
+bad = 0
+crc_ok = 0
+for i in range(300):
+    for c in range(0, 64, 9):
+        w = util.try_clock_one(O, "orc", s, int(pkh[i]["offset"]), int(pkh[i]["length"]), c)
+        bad += w.tobytes() != got[i * 64 + c].tobytes()
+    crc_ok += int((got[i * 64:(i + 1) * 64]["rv"] >= 10).any())
+res["parity_sample"] = {"records_checked": 300 * 8, "mismatches": int(bad), "packets_with_a_crc_clean_clock": crc_ok}
+print(json.dumps(res))

@@ -37,7 +37,8 @@ cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
 ctx = B.Context(0, args.k)
 st = torch.cuda.current_stream().cuda_stream
 out = {"symbols": n, "k": args.k}
-for mode in ("v1", "v3", "v4"):
+MODES = os.environ.get("KBENCH_MODES", "v1,v3,v4a,v4b,v4c,v4d,v4e,v4f").split(",")
+for mode in MODES:
     os.environ["BTBB_B200_SCAN"] = mode
     for _ in range(3):
         B.check(lib.btbb_b200_find_ac_enqueue(ctx.h, ptr, n, B.LAP_ANY, args.k, hits.data_ptr(), cap, cnt.data_ptr(), st))
@@ -55,5 +56,5 @@ for mode in ("v1", "v3", "v4"):
         c, rc = ctx.find_ac_dev(ptr, n, hits.data_ptr(), cap, k=args.k)
         out[mode]["sha"] = __import__("hashlib").sha256(hits[:c].cpu().numpy().tobytes()).hexdigest()[:16]
 if args.check:
-    out["match"] = all(out[m]["sha"] == out["v1"]["sha"] and out[m]["hits"] == out["v1"]["hits"] for m in ("v3", "v4"))
+    out["match"] = all(out[m]["sha"] == out[MODES[0]]["sha"] and out[m]["hits"] == out[MODES[0]]["hits"] for m in MODES)
 print(json.dumps(out))
