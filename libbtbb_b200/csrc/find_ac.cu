@@ -299,53 +299,72 @@ __global__ void __launch_bounds__(NT) scan_known_kernel(const scan_args a)
 	}
 }
 
-/* ---------------- ordering pass: LSD radix sort of 16-byte hit records by offset ---------------- */
+/* ---------------- ordering pass: LSD radix sort of 16-byte hit records by offset (9-bit digits) ---------------- */
 constexpr int SORT_CHUNK = 2048;   /* records per warp */
+constexpr int SORT_BITS = 9;       /* digit width: offsets below 2^36 sort in 4 passes */
+constexpr int SORT_BINS = 1 << SORT_BITS;
 
 __global__ void sort_hist_kernel(const btbb_b200_hit *in, int64_t n, int shift, uint32_t *hist, int nblk)
 {
-	__shared__ uint32_t h[256];
-	for (int i = threadIdx.x; i < 256; i += 32) h[i] = 0;
+	__shared__ uint32_t h[SORT_BINS];
+	for (int i = threadIdx.x; i < SORT_BINS; i += 32) h[i] = 0;
 	__syncwarp();
 	int64_t b0 = (int64_t)blockIdx.x * SORT_CHUNK, b1 = b0 + SORT_CHUNK < n ? b0 + SORT_CHUNK : n;
 	for (int64_t i = b0 + threadIdx.x; i < b1; i += 32)
-		atomicAdd(&h[(uint32_t)((uint64_t)in[i].offset >> shift) & 255u], 1u);
+		atomicAdd(&h[(uint32_t)((uint64_t)in[i].offset >> shift) & (SORT_BINS - 1)], 1u);
 	__syncwarp();
-	for (int i = threadIdx.x; i < 256; i += 32) hist[(int64_t)i * nblk + blockIdx.x] = h[i];
+	for (int i = threadIdx.x; i < SORT_BINS; i += 32) hist[(int64_t)i * nblk + blockIdx.x] = h[i];
 }
 
-/* exclusive scan of `len` counters in place, one block */
-__global__ void sort_scan_kernel(uint32_t *v, int64_t len)
+/* hist is [digit][block]: one warp per digit turns its row into an exclusive scan over the
+ * blocks (coalesced) and leaves the digit's total in tot[digit] */
+__global__ void __launch_bounds__(256) sort_rowscan_kernel(uint32_t *hist, int nblk, uint32_t *tot)
 {
-	__shared__ uint32_t part[1024];
-	__shared__ uint32_t carry;
-	if (threadIdx.x == 0) carry = 0;
-	__syncthreads();
-	for (int64_t base = 0; base < len; base += 1024) {
-		int64_t i = base + threadIdx.x;
-		uint32_t x = i < len ? v[i] : 0;
-		part[threadIdx.x] = x;
-		__syncthreads();
-		for (int d = 1; d < 1024; d <<= 1) {
-			uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
-			__syncthreads();
-			part[threadIdx.x] += t;
-			__syncthreads();
+	const int d = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+	if (d >= SORT_BINS) return;
+	uint32_t *row = hist + (int64_t)d * nblk;
+	uint32_t carry = 0;
+	for (int b0 = 0; b0 < nblk; b0 += 32) {
+		const int b = b0 + lane;
+		const uint32_t x = b < nblk ? row[b] : 0;
+		uint32_t inc = x;
+		#pragma unroll
+		for (int s = 1; s < 32; s <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, s);
+			if (lane >= s) inc += u;
 		}
-		uint32_t incl = part[threadIdx.x];
-		if (i < len) v[i] = carry + incl - x;
-		__syncthreads();
-		if (threadIdx.x == 1023) carry += incl;
-		__syncthreads();
+		if (b < nblk) row[b] = carry + inc - x;
+		carry += __shfl_sync(0xffffffffu, inc, 31);
 	}
+	if (lane == 0) tot[d] = carry;
 }
 
 __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out, int64_t n, int shift,
-				    const uint32_t *hist, int nblk)
+				    const uint32_t *hist, int nblk, const uint32_t *tot)
 {
-	__shared__ uint32_t cur[256];
+	__shared__ uint32_t cur[SORT_BINS];
 	const int lane = threadIdx.x;
-	for (int i = lane; i < 256; i += 32) cur[i] = hist[(int64_t)i * nblk + blockIdx.x];
+	/* start of digit d = sum of the totals of all smaller digits: scan the 512 totals here
+	 * (16 per lane) instead of launching one more kernel */
+	{
+		constexpr int PER = SORT_BINS / 32;
+		uint32_t loc[PER], sum = 0;
+		#pragma unroll
+		for (int i = 0; i < PER; i++) { loc[i] = tot[lane * PER + i]; sum += loc[i]; }
+		uint32_t inc = sum;
+		#pragma unroll
+		for (int s = 1; s < 32; s <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, inc, s);
+			if (lane >= s) inc += u;
+		}
+		uint32_t run = inc - sum;
+		#pragma unroll
+		for (int i = 0; i < PER; i++) {
+			const int d = lane * PER + i;
+			cur[d] = run + hist[(int64_t)d * nblk + blockIdx.x];
+			run += loc[i];
+		}
+	}
 	__syncwarp();
 	int64_t b0 = (int64_t)blockIdx.x * SORT_CHUNK, b1 = b0 + SORT_CHUNK < n ? b0 + SORT_CHUNK : n;
 	for (int64_t i0 = b0; i0 < b1; i0 += 32) {
@@ -353,7 +372,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 		bool live = i < b1;
 		btbb_b200_hit rec;
 		uint32_t dig = 0;
-		if (live) { rec = in[i]; dig = (uint32_t)((uint64_t)rec.offset >> shift) & 255u; }
+		if (live) { rec = in[i]; dig = (uint32_t)((uint64_t)rec.offset >> shift) & (SORT_BINS - 1); }
 		unsigned act = __ballot_sync(0xffffffffu, live);
 		if (live) {
 			unsigned peers = __match_any_sync(act, dig);
@@ -443,7 +462,11 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	if (lap != BTBB_B200_LAP_ANY || !ctx->d_map2 || force_v1)
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	const int64_t head = (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);
-	const int64_t nstrips = n > head ? (n - head) / v3::STRIP : 0;
+	int64_t nstrips = n > head ? (n - head) / v3::STRIP : 0;
+	/* the bulk kernels carry 32-bit positions relative to a warp's run: keep a launch below
+	 * 2^31 symbols per warp (148 x 32 warps -> ~10^13 symbols); beyond that the tail kernel
+	 * below simply takes the rest */
+	if (nstrips > ((int64_t)1 << 31) / v3::STRIP * 4096) nstrips = ((int64_t)1 << 31) / v3::STRIP * 4096;
 	if (nstrips < 1)
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	const int64_t body_end = head + nstrips * v3::STRIP;
@@ -479,8 +502,9 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 		else if (env && !strcmp(env, "v4d")) kern = v4::scan_promisc_v4<0, 5, true>;
 		else if (env && !strcmp(env, "v4e")) kern = v4::scan_promisc_v4<1, 6, true>;
 		else if (env && !strcmp(env, "v4f")) kern = v4::scan_promisc_v4<1, 5, false>;
-		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v4::SMEM_BYTES));
-		kern<<<(unsigned)grid, v4::WARPS * 32, v4::SMEM_BYTES, st>>>(a);
+		const size_t smem = v4::SMEM_BYTES;
+		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kern<<<(unsigned)grid, v4::WARPS * 32, smem, st>>>(a);
 	}
 	BT_CUDA_TRY(cudaGetLastError());
 	int rc = BTBB_B200_OK;
@@ -500,9 +524,10 @@ int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t
 	if (have > 0) {
 		int nblk = (int)((have + SORT_CHUNK - 1) / SORT_CHUNK);
 		for (int p = 0; p < passes; p++) {
-			sort_hist_kernel<<<nblk, 32, 0, st>>>(src, have, 8 * p, ctx->d_sort_hist, nblk);
-			sort_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_sort_hist, (int64_t)nblk * 256);
-			sort_scatter_kernel<<<nblk, 32, 0, st>>>(src, dst, have, 8 * p, ctx->d_sort_hist, nblk);
+			sort_hist_kernel<<<nblk, 32, 0, st>>>(src, have, SORT_BITS * p, ctx->d_sort_hist, nblk);
+			uint32_t *tot = ctx->d_sort_hist + (int64_t)nblk * SORT_BINS;
+			sort_rowscan_kernel<<<SORT_BINS / 8, 256, 0, st>>>(ctx->d_sort_hist, nblk, tot);
+			sort_scatter_kernel<<<nblk, 32, 0, st>>>(src, dst, have, SORT_BITS * p, ctx->d_sort_hist, nblk, tot);
 			btbb_b200_hit *t = src; src = dst; dst = t;
 		}
 		BT_CUDA_TRY(cudaGetLastError());
@@ -516,7 +541,7 @@ int bt_sort_passes(int64_t span)
 {
 	int bits = 1;
 	while (bits < 63 && ((int64_t)1 << bits) < span) bits++;
-	return (bits + 7) / 8;
+	return (bits + SORT_BITS - 1) / SORT_BITS;
 }
 
 int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits)
@@ -528,11 +553,11 @@ int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits)
 		ctx->tmp_cap = hits;
 	}
 	int64_t nblk = (hits + SORT_CHUNK - 1) / SORT_CHUNK;
-	if (nblk * 256 > ctx->sort_hist_cap) {
+	if ((nblk + 1) * SORT_BINS > ctx->sort_hist_cap) {
 		if (ctx->d_sort_hist) cudaFree(ctx->d_sort_hist);
 		ctx->d_sort_hist = NULL; ctx->sort_hist_cap = 0;
-		BT_CUDA_TRY(cudaMalloc(&ctx->d_sort_hist, (size_t)nblk * 256 * sizeof(uint32_t)));
-		ctx->sort_hist_cap = nblk * 256;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_sort_hist, (size_t)(nblk + 1) * SORT_BINS * sizeof(uint32_t)));
+		ctx->sort_hist_cap = (nblk + 1) * SORT_BINS;
 	}
 	return BTBB_B200_OK;
 }

@@ -154,9 +154,12 @@ __device__ __noinline__ void flush4(const xparams *xp, uint32_t x_sa, int lane)
 	__syncwarp();
 }
 
+/* rel = symbol index relative to the warp's run; the run's stream position sits in the
+ * warp's exact-queue block (words 93/94) so the hot loops carry 32-bit positions only */
 template <int LUTMODE>
-__device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, int64_t pos, uint32_t lo, uint32_t hi)
+__device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, uint32_t rel, uint32_t lo, uint32_t hi)
 {
+	const int64_t pos = (int64_t)(((uint64_t)lds32o<94 * 4>(x_sa) << 32) | lds32o<93 * 4>(x_sa)) + rel;
 	uint32_t slot;
 	asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(x_sa) : "memory");
 	if (slot < XCAP) {
@@ -171,7 +174,7 @@ __device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, int64_t pos
  * (bfind(0) = -1, the shift below clamps to 0) and are masked out of the final decision. */
 template <int LUTMODE, bool BF>
 __device__ __forceinline__ void slot(uint32_t &c, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t lane4,
-				     const xparams *xp, uint32_t x_sa, int64_t word_pos)
+				     const xparams *xp, uint32_t x_sa, uint32_t word_pos)
 {
 	if (BF) {
 		const uint32_t q = bfind(c);
@@ -216,11 +219,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 	const uint32_t s_sa = SA_WARP + wid * WARP_BYTES;
 	const uint32_t q_sa = s_sa + S_BYTES;
 	const uint32_t qn_sa = x_sa + 95 * 4;                   /* overflow-queue fill level */
-	if (lane == 0) { sts32(x_sa, 0); sts32(qn_sa, 0); }
-	__syncthreads();
-
 	const int64_t gw = (int64_t)blockIdx.x * WARPS + wid, nw = (int64_t)gridDim.x * WARPS;
 	const int64_t s_begin = a.nstrips * gw / nw, s_end = a.nstrips * (gw + 1) / nw;
+	if (lane == 0) {
+		const int64_t run_pos = a.pos0 + s_begin * STRIP;
+		sts32(x_sa, 0); sts32(qn_sa, 0);
+		sts32(x_sa + 93 * 4, (uint32_t)run_pos); sts32(x_sa + 94 * 4, (uint32_t)(run_pos >> 32));
+	}
+	__syncthreads();
 	const uint32_t lane4 = 4 * lane, my_sa = s_sa + lane4;
 
 	for (int64_t s = s_begin; s < s_end; s++) {
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 			}
 		}
 		__syncwarp();
-		const int64_t strip_pos = a.pos0 + s * STRIP;
+		const uint32_t strip_pos = (uint32_t)(s - s_begin) * STRIP;   /* run-relative */
 		/* ---- filter all rows, then the first candidates of every word in place; the rows
 		 * are independent dependency chains, so slot t of all four rows is issued together ---- */
 		uint32_t rem[K], w1[K], w2[K];
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		}
 		const uint32_t t01 = __reduce_add_sync(0xffffffffu, __popc(rem[0]) | (__popc(rem[1]) << 16));
 		const uint32_t t23 = __reduce_add_sync(0xffffffffu, __popc(rem[2]) | (__popc(rem[3]) << 16));
-		const int64_t lane_pos = strip_pos + lane * 32;
+		const uint32_t lane_pos = strip_pos + lane * 32;
 		if (((t01 | t23) & 0xff00ff00u) == 0) {          /* every row holds <= 255 candidates */
 			#pragma unroll
 			for (int t = 0; t < NSLOTS; t++) {
