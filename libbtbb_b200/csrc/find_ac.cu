@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(NT) scan_known_kernel(const scan_args a)
 }
 
 /* ---------------- ordering pass: LSD radix sort of 16-byte hit records by offset (9-bit digits) ---------------- */
-constexpr int SORT_CHUNK = 2048;   /* records per warp */
+constexpr int SORT_CHUNK = 512;    /* records per warp */
 constexpr int SORT_BITS = 9;       /* digit width: offsets below 2^36 sort in 4 passes */
 constexpr int SORT_BINS = 1 << SORT_BITS;
 
