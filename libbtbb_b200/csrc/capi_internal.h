@@ -28,6 +28,8 @@ struct btbb_b200_ctx {
 	uint32_t *d_bloom;           /* bitmap over the low 32 syndrome bits of table entries (+ zero) */
 	int bloom_log2;              /* log2(bits) */
 	uint32_t *d_lut2;            /* bulk kernel: LUT A (codeword bits 32..44) then LUT B (bits 45..56) */
+	uint32_t *d_lut2b;           /* bulk kernel v4 (shipped): LUT A over codeword bits 34..46, LUT B over 47..56 */
+	uint32_t *d_lut3;            /* bulk kernel v4, LUTMODE 2: three field tables (8/8/7 bits of codeword bits 34..56) */
 	uint32_t *d_lut4;            /* bulk kernel v4: four field tables (7/6/6/6 bits of codeword bits 32..56) */
 	uint32_t *d_map2;            /* bulk kernel: 2^19-bit map of reachable low-32 syndromes, both tails (k <= 2) */
 	uint64_t cc[2];              /* 34-bit syndrome of PN ^ (legal tail << 57) */

@@ -493,16 +493,20 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	} else {
 		v4::args a;
 		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
-		a.lut = ctx->d_lut4; a.lut2 = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
+		a.lut = ctx->d_lut4; a.lut2 = ctx->d_lut2b; a.lut3 = ctx->d_lut3; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
 		/* experiment switch (developer): v4a..v4f pick LUT mode / inline slots / branch-free slots */
-		void (*kern)(const v4::args) = v4::scan_promisc_v4<1, 5, true>;
+		void (*kern)(const v4::args) = v4::scan_promisc_v4<2, 5, true>;
+		size_t smem = v4::layout<2>::smem_bytes;
+		if (env && !strncmp(env, "v4", 2) && env[2] >= 'a' && env[2] <= 'f') smem = v4::SMEM_BYTES;
 		if (env && !strcmp(env, "v4a")) kern = v4::scan_promisc_v4<0, 5, false>;
 		else if (env && !strcmp(env, "v4b")) kern = v4::scan_promisc_v4<1, 5, true>;
 		else if (env && !strcmp(env, "v4c")) kern = v4::scan_promisc_v4<1, 4, true>;
 		else if (env && !strcmp(env, "v4d")) kern = v4::scan_promisc_v4<0, 5, true>;
 		else if (env && !strcmp(env, "v4e")) kern = v4::scan_promisc_v4<1, 6, true>;
 		else if (env && !strcmp(env, "v4f")) kern = v4::scan_promisc_v4<1, 5, false>;
-		const size_t smem = v4::SMEM_BYTES;
+		if (env && !strcmp(env, "v4g")) { kern = v4::scan_promisc_v4<2, 5, true>; smem = v4::layout<2>::smem_bytes; }
+		else if (env && !strcmp(env, "v4h")) { kern = v4::scan_promisc_v4<2, 6, true>; smem = v4::layout<2>::smem_bytes; }
+		else if (env && !strcmp(env, "v4i")) { kern = v4::scan_promisc_v4<2, 4, true>; smem = v4::layout<2>::smem_bytes; }
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		kern<<<(unsigned)grid, v4::WARPS * 32, smem, st>>>(a);
 	}

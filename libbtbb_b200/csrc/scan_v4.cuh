@@ -53,13 +53,26 @@ constexpr uint32_t S_BYTES = (SW + 8) * 4;
 constexpr uint32_t WARP_BYTES = S_BYTES + QCAP * 2;
 constexpr uint32_t SA_END = SA_WARP + WARPS * WARP_BYTES;
 constexpr size_t SMEM_BYTES = SA_END;
+/* LUTMODE 2: three lane-private field tables over codeword bits 34..41 / 42..49 / 50..56
+ * (256 + 256 + 128 entries x 128 B = 80 KiB): T0 at 0x4000, T2 at 0xC000, T1 behind the map
+ * at 0x20000; the per-warp blocks move to 0x28000 and the overflow queue shrinks to 512. */
+constexpr uint32_t SA_F0 = 0x4000, SA_F2 = 0xC000, SA_F1 = 0x20000, SA_WARP_M2 = 0x28000;
+constexpr int QCAP_M2 = 512;
+constexpr int LUT3_ENTRIES = 256 + 256 + 128;
+template <int LUTMODE> struct layout {
+	static constexpr uint32_t sa_warp = LUTMODE == 2 ? SA_WARP_M2 : SA_WARP;
+	static constexpr int qcap = LUTMODE == 2 ? QCAP_M2 : QCAP;
+	static constexpr uint32_t warp_bytes = S_BYTES + qcap * 2;
+	static constexpr size_t smem_bytes = sa_warp + WARPS * warp_bytes;
+};
 
 struct args {
 	const uint8_t *base;     /* 32-byte aligned; base[0] is stream position pos0 */
 	int64_t pos0;
 	int64_t nstrips;
 	const uint32_t *lut;     /* LUT_ENTRIES words: the four field tables back to back (LUTMODE 0) */
-	const uint32_t *lut2;    /* v3 layout: LUT A (2^13) then LUT B (2^12) (LUTMODE 1) */
+	const uint32_t *lut3;    /* LUT3_ENTRIES words: three field tables (LUTMODE 2) */
+	const uint32_t *lut2;    /* LUT A (2^13 entries, codeword bits 34..46) then LUT B (2^10, bits 47..56) (LUTMODE 1) */
 	const uint32_t *map;     /* MAP_WORDS */
 	const xparams *xp;
 };
@@ -75,18 +88,36 @@ __device__ __forceinline__ uint32_t syn_lo32(uint32_t lo, uint32_t hi, uint32_t 
 	return lo ^ t0 ^ t1 ^ t2 ^ t3;
 }
 
-/* LUTMODE 1: two shared tables over bits 32..44 / 45..56 (half the instructions, but the
- * lookups collide in the banks like any random access) */
+/* LUTMODE 1: two shared tables over codeword bits 34..46 / 47..56 (bits 32 and 33 pass
+ * straight into syndrome bits 32/33, which the filter does not look at).  Table A's 13
+ * index bits sit at bits 2..14 of `hi`, i.e. already scaled to a byte offset: one LOP3.
+ * Fewer instructions than the lane-private tables, but the lookups collide in the banks
+ * like any random access. */
 __device__ __forceinline__ uint32_t syn_lo32_2(uint32_t lo, uint32_t hi)
 {
-	const uint32_t ta = lds32o<0x8000>((hi << 2) & (8191u << 2));
-	const uint32_t tb = lds32o<0x4000>((hi >> 11) & (4095u << 2));
+	const uint32_t ta = lds32o<0x8000>(hi & (8191u << 2));
+	const uint32_t tb = lds32o<0x4000>((hi >> 13) & (1023u << 2));
 	return lo ^ ta ^ tb;
+}
+/* 1 << q, or 0 when q >= 32 (bfind of an empty mask) */
+__device__ __forceinline__ uint32_t onebit(uint32_t q)
+{
+	uint32_t r;
+	asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(r) : "r"(q));
+	return r;
+}
+/* LUTMODE 2: three conflict-free lookups (bits 32/33 skipped as in LUTMODE 1) */
+__device__ __forceinline__ uint32_t syn_lo32_3(uint32_t lo, uint32_t hi, uint32_t lane4)
+{
+	const uint32_t t0 = lds32o<SA_F0>(((hi << 5) & (255u << 7)) | lane4);
+	const uint32_t t1 = lds32o<SA_F1>(((hi >> 3) & (255u << 7)) | lane4);
+	const uint32_t t2 = lds32o<SA_F2>(((hi >> 11) & (127u << 7)) | lane4);
+	return lo ^ t0 ^ t1 ^ t2;
 }
 template <int LUTMODE>
 __device__ __forceinline__ uint32_t syn32(uint32_t lo, uint32_t hi, uint32_t lane4)
 {
-	return LUTMODE ? syn_lo32_2(lo, hi) : syn_lo32(lo, hi, lane4);
+	return LUTMODE == 1 ? syn_lo32_2(lo, hi) : LUTMODE == 2 ? syn_lo32_3(lo, hi, lane4) : syn_lo32(lo, hi, lane4);
 }
 
 __device__ __forceinline__ uint32_t map_bit(uint32_t sy)
@@ -171,18 +202,18 @@ __device__ __noinline__ void park4(const xparams *xp, uint32_t x_sa, uint32_t re
 
 /* take the highest remaining candidate of this lane's word (if any) and test it in place.
  * BF (branch-free): lanes without a candidate run the same instructions on a dummy window
- * (bfind(0) = -1, the shift below clamps to 0) and are masked out of the final decision. */
+ * (bfind(0) = -1, onebit() then gives 0) and contribute nothing; a map positive only sets
+ * the candidate's bit in `hitm` (one IMAD), the rare follow-up happens once per strip. */
 template <int LUTMODE, bool BF>
-__device__ __forceinline__ void slot(uint32_t &c, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t lane4,
+__device__ __forceinline__ void slot(uint32_t &c, uint32_t &hitm, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t lane4,
 				     const xparams *xp, uint32_t x_sa, uint32_t word_pos)
 {
 	if (BF) {
 		const uint32_t q = bfind(c);
-		uint32_t bit;
-		asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(q));
+		const uint32_t bit = onebit(q);
 		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
-		if (map_bit(syn32<LUTMODE>(lo, hi, lane4)) && bit)
-			park4<LUTMODE>(xp, x_sa, word_pos + q, lo, hi);
+		/* hitm += mapbit * bit as one IMAD (FMA pipe) instead of compare + select + add */
+		asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hitm) : "r"(map_bit(syn32<LUTMODE>(lo, hi, lane4))), "r"(bit));
 		c ^= bit;
 	} else if (c) {
 		const uint32_t q = bfind(c);
@@ -190,6 +221,18 @@ __device__ __forceinline__ void slot(uint32_t &c, uint32_t w0, uint32_t w1, uint
 		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
 		if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
 			park4<LUTMODE>(xp, x_sa, word_pos + q, lo, hi);
+	}
+}
+
+/* the map positives a row collected in its inline slots */
+template <int LUTMODE>
+__device__ __forceinline__ void park_row(uint32_t hitm, uint32_t w0, uint32_t w1, uint32_t w2,
+					 const xparams *xp, uint32_t x_sa, uint32_t word_pos)
+{
+	while (hitm) {
+		const uint32_t q = bfind(hitm);
+		hitm ^= 1u << q;
+		park4<LUTMODE>(xp, x_sa, word_pos + q, __funnelshift_r(w0, w1, q), __funnelshift_r(w1, w2, q));
 	}
 }
 
@@ -210,13 +253,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 					    : e < 256 ? SA_T2 + 128 * (e - 192) : SA_T3 + 128 * (e - 256);
 			sts32(base + 4 * l, a.lut[e]);
 		}
+	} else if (LUTMODE == 2) {
+		for (int i = threadIdx.x; i < LUT3_ENTRIES * 32; i += WARPS * 32) {
+			const int e = i >> 5, l = i & 31;
+			const uint32_t base = e < 256 ? SA_F0 + 128 * e : e < 512 ? SA_F1 + 128 * (e - 256) : SA_F2 + 128 * (e - 512);
+			sts32(base + 4 * l, a.lut3[e]);
+		}
 	} else {
 		for (int i = threadIdx.x; i < 8192; i += WARPS * 32) sts32(0x8000 + 4 * i, a.lut2[i]);
-		for (int i = threadIdx.x; i < 4096; i += WARPS * 32) sts32(0x4000 + 4 * i, a.lut2[8192 + i]);
+		for (int i = threadIdx.x; i < 1024; i += WARPS * 32) sts32(0x4000 + 4 * i, a.lut2[8192 + i]);
 	}
 	for (int i = threadIdx.x; i < MAP_WORDS; i += WARPS * 32) sts32(SA_MAP + 4 * i, a.map[i]);
 	const uint32_t x_sa = SA_X + wid * X_BYTES;
-	const uint32_t s_sa = SA_WARP + wid * WARP_BYTES;
+	const uint32_t s_sa = layout<LUTMODE>::sa_warp + wid * layout<LUTMODE>::warp_bytes;
 	const uint32_t q_sa = s_sa + S_BYTES;
 	const uint32_t qn_sa = x_sa + 95 * 4;                   /* overflow-queue fill level */
 	const int64_t gw = (int64_t)blockIdx.x * WARPS + wid, nw = (int64_t)gridDim.x * WARPS;
@@ -263,18 +312,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		const uint32_t t23 = __reduce_add_sync(0xffffffffu, __popc(rem[2]) | (__popc(rem[3]) << 16));
 		const uint32_t lane_pos = strip_pos + lane * 32;
 		if (((t01 | t23) & 0xff00ff00u) == 0) {          /* every row holds <= 255 candidates */
+			uint32_t hitm[K] = {0, 0, 0, 0};
 			#pragma unroll
 			for (int t = 0; t < NSLOTS; t++) {
 				#pragma unroll
 				for (int k = 0; k < K; k++)
-					slot<LUTMODE, BF>(rem[k], wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
+					slot<LUTMODE, BF>(rem[k], hitm[k], wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
+			}
+			if (BF && (hitm[0] | hitm[1] | hitm[2] | hitm[3])) {
+				#pragma unroll
+				for (int k = 0; k < K; k++)
+					park_row<LUTMODE>(hitm[k], wv[k], w1[k], w2[k], xp, x_sa, lane_pos + k * 1024);
 			}
 		} else {
 			#pragma unroll
 			for (int k = 0; k < K; k++) {
 				uint32_t c = rem[k];
+				uint32_t dummy = 0;
 				while (__any_sync(0xffffffffu, c != 0))
-					slot<LUTMODE, false>(c, wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
+					slot<LUTMODE, false>(c, dummy, wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
 				rem[k] = 0;
 			}
 		}
@@ -282,9 +338,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		 * A lane reserves its entries with one shared-memory atomic (a row holds at most 255
 		 * candidates here, so the queue cannot overflow). ---- */
 		if (__any_sync(0xffffffffu, (rem[0] | rem[1] | rem[2] | rem[3]) != 0)) {
+		    /* a row holds <= 255 candidates here, i.e. <= 250 beyond the slots: four rows always
+		     * fit a 1024-entry queue, two rows always fit a 512-entry one */
+		    const uint32_t ov = layout<LUTMODE>::qcap >= 1024 ? 0u :
+			__reduce_add_sync(0xffffffffu, __popc(rem[0]) + __popc(rem[1]) + __popc(rem[2]) + __popc(rem[3]));
+		    const int npass = ov > (uint32_t)layout<LUTMODE>::qcap ? 2 : 1;
+		    for (int pass = 0; pass < npass; pass++) {
 			#pragma unroll
 			for (int k = 0; k < K; k++) {
-				uint32_t m = rem[k];
+				uint32_t m = (npass == 1 || (k >> 1) == pass) ? rem[k] : 0u;
 				if (m) {
 					uint32_t at;
 					asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(at) : "r"(qn_sa), "r"(__popc(m)) : "memory");
@@ -310,6 +372,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 			}
 			__syncwarp();
 			if (lane == 0) sts32(qn_sa, 0);
+			__syncwarp();
+		    }
 		}
 		__syncwarp();
 		if (lds32(x_sa) >= XCAP / 2) flush4<LUTMODE>(xp, x_sa, lane);

@@ -73,7 +73,7 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	 * bits, bit = low 5) of every value that part can take for an acceptable window: the
 	 * table syndromes (and zero) XOR the constant of either legal tail.  Only built while the
 	 * map stays sparse (k <= 2: at most 3424 of 2^19 bits set). --- */
-	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL;
+	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL; ctx->d_lut2b = NULL; ctx->d_lut3 = NULL;
 	ctx->cc[0] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_A << 57));
 	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
 	ctx->m32 = ctx->m33 = 0;
@@ -94,7 +94,37 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 			for (int j = 0; j < bbits; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + abits + j];
 			lut[((size_t)1 << abits) + v] = (uint32_t)sy;
 		}
-		/* v4: the same 25 bits as four lane-replicated field tables (7, 6, 6, 6 bits) */
+		/* v4, LUTMODE 1: bits 34..46 (13) and 47..56 (10); bits 32/33 do not reach the low 32
+		 * syndrome bits */
+		{
+			std::vector<uint32_t> l2b(8192 + 1024, 0u);
+			for (uint32_t v = 0; v < 8192; v++) {
+				uint64_t sy = 0;
+				for (int j = 0; j < 13; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + j];
+				l2b[v] = (uint32_t)sy;
+			}
+			for (uint32_t v = 0; v < 1024; v++) {
+				uint64_t sy = 0;
+				for (int j = 0; j < 10; j++) if ((v >> j) & 1) sy ^= g_bit_syn[47 + j];
+				l2b[8192 + v] = (uint32_t)sy;
+			}
+			BT_CUDA_TRY(cudaMalloc(&ctx->d_lut2b, l2b.size() * sizeof(uint32_t)));
+			BT_CUDA_TRY(cudaMemcpy(ctx->d_lut2b, l2b.data(), l2b.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		}
+		/* v4, LUTMODE 2: bits 34..41 / 42..49 / 50..56 as three lane-replicated field tables */
+		{
+			std::vector<uint32_t> l3;
+			const int fw3[3] = {8, 8, 7};
+			for (int f = 0, pos = 0; f < 3; pos += fw3[f], f++)
+				for (uint32_t v = 0; v < (1u << fw3[f]); v++) {
+					uint64_t sy = 0;
+					for (int j = 0; j < fw3[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + pos + j];
+					l3.push_back((uint32_t)sy);
+				}
+			BT_CUDA_TRY(cudaMalloc(&ctx->d_lut3, l3.size() * sizeof(uint32_t)));
+			BT_CUDA_TRY(cudaMemcpy(ctx->d_lut3, l3.data(), l3.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		}
+		/* v4, LUTMODE 0: the same 25 bits as four lane-replicated field tables (7, 6, 6, 6 bits) */
 		std::vector<uint32_t> lut4;
 		const int fw[4] = {7, 6, 6, 6};
 		for (int f = 0, pos = 0; f < 4; pos += fw[f], f++)
@@ -147,6 +177,8 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_lut2) cudaFree(ctx->d_lut2);
 	if (ctx->d_map2) cudaFree(ctx->d_map2);
 	if (ctx->d_lut4) cudaFree(ctx->d_lut4);
+	if (ctx->d_lut2b) cudaFree(ctx->d_lut2b);
+	if (ctx->d_lut3) cudaFree(ctx->d_lut3);
 	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
-	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL;
+	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL; ctx->d_lut2b = NULL; ctx->d_lut3 = NULL;
 }
