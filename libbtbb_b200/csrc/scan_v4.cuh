@@ -288,11 +288,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 			for (int k = 0; k < K; k++) ld256(p + k * 1024, raw[k]);
 			#pragma unroll
 			for (int k = 0; k < K; k++) { wv[k] = pack32(raw[k]); sts32(my_sa + 128 * k, wv[k]); }
-			if (lane < 2) {        /* 64-symbol halo = first two words of the next strip */
+			if (lane < 2) {        /* 64-symbol halo = first two words of the next strip (L2-resident) */
 				ld256(p + STRIP, raw[0]);
 				sts32(my_sa + 128 * K, pack32(raw[0]));
 			}
-			if (s + 1 < s_end) {
+			if (s + 1 < s_end) {   /* pull the next strip into L2 while this one is processed */
 				#pragma unroll
 				for (int k = 0; k < K; k++)
 					asm volatile("prefetch.global.L2 [%0];" :: "l"(p + STRIP + k * 1024));
@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		}
 		__syncwarp();
 		const uint32_t strip_pos = (uint32_t)(s - s_begin) * STRIP;   /* run-relative */
+		const uint32_t lane_pos = strip_pos + lane * 32;
 		/* ---- filter all rows, then the first candidates of every word in place; the rows
 		 * are independent dependency chains, so slot t of all four rows is issued together ---- */
 		uint32_t rem[K], w1[K], w2[K];
@@ -308,10 +309,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 			w1[k] = lds32(my_sa + 128 * k + 4); w2[k] = lds32(my_sa + 128 * k + 8);
 			rem[k] = barker_mask(w1[k], w2[k]);
 		}
-		const uint32_t t01 = __reduce_add_sync(0xffffffffu, __popc(rem[0]) | (__popc(rem[1]) << 16));
-		const uint32_t t23 = __reduce_add_sync(0xffffffffu, __popc(rem[2]) | (__popc(rem[3]) << 16));
-		const uint32_t lane_pos = strip_pos + lane * 32;
-		if (((t01 | t23) & 0xff00ff00u) == 0) {          /* every row holds <= 255 candidates */
+		{
 			uint32_t hitm[K] = {0, 0, 0, 0};
 			#pragma unroll
 			for (int t = 0; t < NSLOTS; t++) {
@@ -324,56 +322,49 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 				for (int k = 0; k < K; k++)
 					park_row<LUTMODE>(hitm[k], wv[k], w1[k], w2[k], xp, x_sa, lane_pos + k * 1024);
 			}
-		} else {
-			#pragma unroll
-			for (int k = 0; k < K; k++) {
-				uint32_t c = rem[k];
-				uint32_t dummy = 0;
-				while (__any_sync(0xffffffffu, c != 0))
-					slot<LUTMODE, false>(c, dummy, wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
-				rem[k] = 0;
-			}
 		}
-		/* ---- the few candidates beyond the inline slots: queue + all-lanes-busy consumer.
-		 * A lane reserves its entries with one shared-memory atomic (a row holds at most 255
-		 * candidates here, so the queue cannot overflow). ---- */
-		if (__any_sync(0xffffffffu, (rem[0] | rem[1] | rem[2] | rem[3]) != 0)) {
-		    /* a row holds <= 255 candidates here, i.e. <= 250 beyond the slots: four rows always
-		     * fit a 1024-entry queue, two rows always fit a 512-entry one */
-		    const uint32_t ov = layout<LUTMODE>::qcap >= 1024 ? 0u :
-			__reduce_add_sync(0xffffffffu, __popc(rem[0]) + __popc(rem[1]) + __popc(rem[2]) + __popc(rem[3]));
-		    const int npass = ov > (uint32_t)layout<LUTMODE>::qcap ? 2 : 1;
-		    for (int pass = 0; pass < npass; pass++) {
-			#pragma unroll
-			for (int k = 0; k < K; k++) {
-				uint32_t m = (npass == 1 || (k >> 1) == pass) ? rem[k] : 0u;
-				if (m) {
-					uint32_t at;
-					asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(at) : "r"(qn_sa), "r"(__popc(m)) : "memory");
-					uint32_t dst = q_sa + 2 * at;
-					const uint32_t ebase = (uint32_t)(k * 32 + lane) << 7;
-					do {
-						const uint32_t q0 = bfind(m);
-						m ^= 1u << q0;
-						sts16o<0>(dst, ebase | q0);
-						dst += 2;
-					} while (m);
+		/* ---- candidates beyond the inline slots (7 %) ---- */
+		const uint32_t mine = __popc(rem[0]) + __popc(rem[1]) + __popc(rem[2]) + __popc(rem[3]);
+		if (__any_sync(0xffffffffu, mine != 0)) {
+			const uint32_t ov = __reduce_add_sync(0xffffffffu, mine);
+			if (ov > (uint32_t)layout<LUTMODE>::qcap) {
+				/* more than the queue holds: adversarial input only -- finish in place */
+				#pragma unroll
+				for (int k = 0; k < K; k++) {
+					uint32_t c = rem[k], dummy = 0;
+					while (__any_sync(0xffffffffu, c != 0))
+						slot<LUTMODE, false>(c, dummy, wv[k], w1[k], w2[k], lane4, xp, x_sa, lane_pos + k * 1024);
 				}
+			} else {
+				/* queue + all-lanes-busy consumer; one shared atomic per lane reserves its entries */
+				if (mine) {
+					uint32_t at;
+					asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(at) : "r"(qn_sa), "r"(mine) : "memory");
+					uint32_t dst = q_sa + 2 * at;
+					#pragma unroll
+					for (int k = 0; k < K; k++) {
+						uint32_t m = rem[k];
+						const uint32_t ebase = (uint32_t)(k * 32 + lane) << 7;
+						while (m) {
+							const uint32_t q0 = bfind(m);
+							m ^= 1u << q0;
+							sts16o<0>(dst, ebase | q0);
+							dst += 2;
+						}
+					}
+				}
+				__syncwarp();
+				for (uint32_t i = lane; i < ov; i += 32) {
+					const uint32_t e = lds16o<0>(q_sa + 2 * i);
+					const uint32_t wa = s_sa + (e >> 5);
+					const uint32_t w0 = lds32o<0>(wa), x1 = lds32o<4>(wa), x2 = lds32o<8>(wa);
+					const uint32_t lo = __funnelshift_r(w0, x1, e), hi = __funnelshift_r(x1, x2, e);
+					if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
+						park4<LUTMODE>(xp, x_sa, strip_pos + (e >> 7) * 32 + (e & 31), lo, hi);
+				}
+				__syncwarp();
+				if (lane == 0) sts32(qn_sa, 0);
 			}
-			__syncwarp();
-			const uint32_t nq = lds32(qn_sa);
-			for (uint32_t i = lane; i < nq; i += 32) {
-				const uint32_t e = lds16o<0>(q_sa + 2 * i);
-				const uint32_t wa = s_sa + (e >> 5);
-				const uint32_t w0 = lds32o<0>(wa), w1 = lds32o<4>(wa), w2 = lds32o<8>(wa);
-				const uint32_t lo = __funnelshift_r(w0, w1, e), hi = __funnelshift_r(w1, w2, e);
-				if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
-					park4<LUTMODE>(xp, x_sa, strip_pos + (e >> 7) * 32 + (e & 31), lo, hi);
-			}
-			__syncwarp();
-			if (lane == 0) sts32(qn_sa, 0);
-			__syncwarp();
-		    }
 		}
 		__syncwarp();
 		if (lds32(x_sa) >= XCAP / 2) flush4<LUTMODE>(xp, x_sa, lane);
