@@ -240,10 +240,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / steps
     value = total_positions / (ms_step / 1e3) / 1e9
-    passes = 1
-    while passes < 8 and (1 << (9 * passes)) < n:
-        passes += 1
-    launches_per_step = 1 + (3 * passes if local_hits else 0)
+    # kernels of this library launched per step: bulk scan, tile kernel on the ragged tail,
+    # slab_scan + slab_sort (ordering)
+    launches_per_step = 4
 
     # ---- roofline of the dominant kernel: the scan alone, CUDA events on its stream ----
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]

@@ -34,6 +34,10 @@ struct btbb_b200_ctx {
 	uint32_t *d_map2;            /* bulk kernel: 2^19-bit map of reachable low-32 syndromes, both tails (k <= 2) */
 	uint64_t cc[2];              /* 34-bit syndrome of PN ^ (legal tail << 57) */
 	uint32_t m32, m33;           /* parity masks over codeword bits 32..56 for syndrome bits 32 / 33 */
+	btbb_b200_hit *d_slab;       /* slab ordering: (warps + 2) x BT_SLAB_CAP records */
+	uint32_t *d_slab_cnt;        /* per-slab fill counts (+ two 64-bit edge counters) */
+	unsigned long long *d_slab_base;
+	int slab_n;
 	void *d_xp;                  /* ring of 16 x 128-byte exact-test parameter blocks (bulk kernel) */
 	unsigned xp_next;
 	bt_err_slot *d_err;          /* hash table, capacity 1 << err_log2 (NULL when table_k == 0) */
@@ -62,6 +66,12 @@ int bt_tables_build(btbb_b200_ctx *ctx, int max_ac_errors);
 void bt_tables_free(btbb_b200_ctx *ctx);
 
 /* find_ac.cu */
+#define BT_SLAB_CAP 1024
+struct bt_slab_req { int used, nw; };
+int bt_ensure_slab(btbb_b200_ctx *ctx, int nslabs);
+int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
+		      btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
+		      int64_t bias, cudaStream_t st, bt_slab_req *slab);
 int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits);
 int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,

@@ -456,6 +456,16 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
 		   int64_t bias, cudaStream_t st)
 {
+	return bt_scan_launch_ex(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st, NULL);
+}
+
+/* slab != NULL: try slab mode (promiscuous bulk path only); *slab->used tells the caller
+ * whether it was taken and how many warps the bulk kernel ran with. */
+int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
+		      btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
+		      int64_t bias, cudaStream_t st, bt_slab_req *slab)
+{
+	if (slab) slab->used = 0;
 	const char *env = getenv("BTBB_B200_SCAN");
 	const bool force_v1 = env && !strcmp(env, "v1");
 	if (n <= 0) return BTBB_B200_OK;
@@ -476,14 +486,23 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	xp.m32 = ctx->m32; xp.m33 = ctx->m33;
 	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err;
 	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
+	int64_t grid = ctx->sm_count;
+	const int64_t need = (nstrips + v3::WARPS - 1) / v3::WARPS;
+	if (grid > need) grid = need;
+	const bool slab_mode = slab && !(env && !strcmp(env, "v3")) && !(env && !strcmp(env, "noslab"));
+	if (slab_mode) {
+		const int nw = (int)grid * v4::WARPS;
+		int rc2 = bt_ensure_slab(ctx, nw + 2);
+		if (rc2) return rc2;
+		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_slab_cnt, 0, (size_t)(nw + 2) * sizeof(uint32_t) + 2 * sizeof(unsigned long long), st));
+		xp.slab = ctx->d_slab; xp.slab_cnt = ctx->d_slab_cnt; xp.slab_cap = BT_SLAB_CAP;
+		slab->used = 1; slab->nw = nw;
+	}
 	if (!ctx->d_xp)
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_xp, 16 * 128));
 	static_assert(sizeof(v3::xparams) <= 128, "xparams slot");
 	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
 	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
-	int64_t grid = ctx->sm_count;
-	const int64_t need = (nstrips + v3::WARPS - 1) / v3::WARPS;
-	if (grid > need) grid = need;
 	if (env && !strcmp(env, "v3")) {
 		v3::args a;
 		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
@@ -512,6 +531,17 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 	}
 	BT_CUDA_TRY(cudaGetLastError());
 	int rc = BTBB_B200_OK;
+	if (slab_mode) {
+		/* head / tail go to slabs nw and nw+1; their 64-bit counters sit behind the 32-bit ones */
+		const int nw = slab->nw;
+		unsigned long long *edge_cnt = (unsigned long long *)(ctx->d_slab_cnt + ((nw + 2 + 1) & ~1));
+		if (head > 0)
+			rc = scan_launch_v1(ctx, d_stream, head, lap, k, ctx->d_slab + (size_t)nw * BT_SLAB_CAP, BT_SLAB_CAP, edge_cnt, bias, st);
+		if (!rc && body_end < n)
+			rc = scan_launch_v1(ctx, d_stream + body_end, n - body_end, lap, k, ctx->d_slab + (size_t)(nw + 1) * BT_SLAB_CAP,
+					    BT_SLAB_CAP, edge_cnt + 1, bias + body_end, st);
+		return rc;
+	}
 	if (head > 0)
 		rc = scan_launch_v1(ctx, d_stream, head, lap, k, d_out, max_hits, d_count, bias, st);
 	if (!rc && body_end < n)
@@ -538,6 +568,127 @@ int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t
 	} else if (passes & 1)
 		src = b;
 	*result = src;
+	return BTBB_B200_OK;
+}
+
+/* ---------------- slab ordering: per-warp slabs -> ascending list ---------------- */
+namespace {
+
+/* one block: slab order is head (index nw), runs 0..nw-1, tail (nw+1).  Writes the exclusive
+ * bases (64-bit) into base[0..nw+2), the total into out[0] and an overflow flag into out[1]. */
+__global__ void __launch_bounds__(1024) slab_scan_kernel(uint32_t *cnt, const unsigned long long *edge, int nw,
+							 unsigned long long *base, unsigned long long *out)
+{
+	__shared__ unsigned long long wsum[32];
+	__shared__ unsigned long long carry_s;
+	__shared__ int over;
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	if (t == 0) {
+		carry_s = 0; over = 0;
+		/* fold the 64-bit edge counters into the 32-bit array */
+		const unsigned long long h = edge[0], tl = edge[1];
+		if (h > BT_SLAB_CAP || tl > BT_SLAB_CAP) over = 1;
+		cnt[nw] = (uint32_t)(h > BT_SLAB_CAP ? BT_SLAB_CAP : h);
+		cnt[nw + 1] = (uint32_t)(tl > BT_SLAB_CAP ? BT_SLAB_CAP : tl);
+	}
+	__syncthreads();
+	const int total = nw + 2;
+	for (int b0 = 0; b0 < total; b0 += 1024) {
+		const int pos = b0 + t;                       /* position in output order */
+		const int idx = pos == 0 ? nw : (pos <= nw ? pos - 1 : nw + 1);
+		unsigned long long x = 0;
+		if (pos < total) {
+			uint32_t c = cnt[idx];
+			if (c > BT_SLAB_CAP) { over = 1; c = BT_SLAB_CAP; }
+			x = c;
+		}
+		unsigned long long inc = x;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += u;
+		}
+		if (lane == 31) wsum[w] = inc;
+		__syncthreads();
+		if (w == 0) {
+			unsigned long long y = wsum[lane], z = y;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned long long u = __shfl_up_sync(0xffffffffu, z, d);
+				if (lane >= d) z += u;
+			}
+			wsum[lane] = z - y;
+		}
+		__syncthreads();
+		const unsigned long long excl = carry_s + wsum[w] + inc - x;
+		if (pos < total) base[idx] = excl;
+		__syncthreads();
+		if (t == 1023) carry_s = excl + x;
+		__syncthreads();
+	}
+	if (t == 0) { out[0] = carry_s; out[1] = (unsigned long long)over; }
+}
+
+/* one block per slab: bitonic sort of <= BT_SLAB_CAP records by offset, written to its place */
+__global__ void __launch_bounds__(256) slab_sort_kernel(const btbb_b200_hit *slab, const uint32_t *cnt,
+							const unsigned long long *base, btbb_b200_hit *out, int64_t max_hits)
+{
+	__shared__ long long key[BT_SLAB_CAP];
+	__shared__ unsigned long long val[BT_SLAB_CAP];
+	const int s = blockIdx.x;
+	uint32_t n = cnt[s];
+	if (n == 0) return;
+	if (n > BT_SLAB_CAP) n = BT_SLAB_CAP;
+	uint32_t N = 32;
+	while (N < n) N <<= 1;
+	const btbb_b200_hit *src = slab + (size_t)s * BT_SLAB_CAP;
+	for (uint32_t i = threadIdx.x; i < N; i += 256) {
+		if (i < n) {
+			const btbb_b200_hit h = src[i];
+			key[i] = h.offset; val[i] = ((unsigned long long)h.lap << 8) | h.ac_errors;
+		} else { key[i] = 0x7fffffffffffffffLL; val[i] = 0; }
+	}
+	__syncthreads();
+	for (uint32_t k = 2; k <= N; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			for (uint32_t i = threadIdx.x; i < N; i += 256) {
+				const uint32_t l = i ^ j;
+				if (l > i) {
+					const bool up = (i & k) == 0;
+					const long long a = key[i], b = key[l];
+					if ((a > b) == up) {
+						key[i] = b; key[l] = a;
+						const unsigned long long t = val[i]; val[i] = val[l]; val[l] = t;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	const unsigned long long b0 = base[s];
+	for (uint32_t i = threadIdx.x; i < n; i += 256) {
+		if ((int64_t)(b0 + i) < max_hits) {
+			btbb_b200_hit h;
+			h.offset = key[i]; h.lap = (uint32_t)(val[i] >> 8); h.ac_errors = (uint8_t)(val[i] & 0xff);
+			h.pad[0] = h.pad[1] = h.pad[2] = 0;
+			out[b0 + i] = h;
+		}
+	}
+}
+
+}  // namespace
+
+int bt_ensure_slab(btbb_b200_ctx *ctx, int nslabs)
+{
+	if (nslabs > ctx->slab_n) {
+		if (ctx->d_slab) cudaFree(ctx->d_slab);
+		if (ctx->d_slab_cnt) cudaFree(ctx->d_slab_cnt);
+		if (ctx->d_slab_base) cudaFree(ctx->d_slab_base);
+		ctx->d_slab = NULL; ctx->d_slab_cnt = NULL; ctx->d_slab_base = NULL; ctx->slab_n = 0;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_slab, (size_t)nslabs * BT_SLAB_CAP * sizeof(btbb_b200_hit)));
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_slab_cnt, (size_t)(nslabs + 2) * sizeof(uint32_t) + 2 * sizeof(unsigned long long)));
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_slab_base, (size_t)nslabs * sizeof(unsigned long long)));
+		ctx->slab_n = nslabs;
+	}
 	return BTBB_B200_OK;
 }
 
@@ -591,14 +742,59 @@ extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream
 	*n_hits = 0;
 	int rc = bt_ensure_tmp(ctx, max_hits > 0 ? max_hits : 1);
 	if (rc) return rc;
-	/* the scan writes into whichever buffer makes the last scatter land in d_hits */
+	unsigned long long total = 0;
+	/* fast ordering: per-warp slabs, one small sort per slab (promiscuous bulk path only) */
+	if (lap == BTBB_B200_LAP_ANY) {
+		bt_slab_req req;
+		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(unsigned long long), st));
+		rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, 0, st, &req);
+		if (rc) return rc;
+		if (req.used) {
+			const int nw = req.nw;
+			unsigned long long *edge_cnt = (unsigned long long *)(ctx->d_slab_cnt + ((nw + 2 + 1) & ~1));
+			slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count);
+			unsigned long long res2[2] = {0, 0};
+			BT_CUDA_TRY(cudaMemcpyAsync(res2, ctx->d_count, sizeof(res2), cudaMemcpyDeviceToHost, st));
+			BT_CUDA_TRY(cudaStreamSynchronize(st));
+			if (res2[0] >> 62)
+				return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
+			if (!res2[1]) {
+				total = res2[0];
+				*n_hits = (int64_t)total;
+				slab_sort_kernel<<<nw + 2, 256, 0, st>>>(ctx->d_slab, ctx->d_slab_cnt, ctx->d_slab_base, d_hits, max_hits);
+				BT_CUDA_TRY(cudaGetLastError());
+				BT_CUDA_TRY(cudaStreamSynchronize(st));
+				if ((int64_t)total > max_hits)
+					return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
+				return BTBB_B200_OK;
+			}
+			/* a slab overflowed (very dense hits): fall through to the generic path */
+		} else {
+			/* slab mode not taken: the launch above already produced the unordered list in d_tmp */
+			BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
+			BT_CUDA_TRY(cudaStreamSynchronize(st));
+			if (total >> 62)
+				return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
+			*n_hits = (int64_t)total;
+			int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
+			btbb_b200_hit *res = NULL;
+			rc = bt_sort_hits(ctx, ctx->d_tmp, d_hits, have, bt_sort_passes(search_length), st, &res);
+			if (rc) return rc;
+			if (res != d_hits && have > 0)
+				BT_CUDA_TRY(cudaMemcpyAsync(d_hits, res, (size_t)have * sizeof(btbb_b200_hit), cudaMemcpyDeviceToDevice, st));
+			BT_CUDA_TRY(cudaStreamSynchronize(st));
+			if ((int64_t)total > max_hits)
+				return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
+			return BTBB_B200_OK;
+		}
+	}
+	/* generic path: the scan writes into whichever buffer makes the last scatter land in d_hits */
 	int passes = bt_sort_passes(search_length);
 	btbb_b200_hit *first = (passes & 1) ? ctx->d_tmp : d_hits;
 	btbb_b200_hit *other = (passes & 1) ? d_hits : ctx->d_tmp;
 	BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
 	rc = bt_scan_launch(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, 0, st);
 	if (rc) return rc;
-	unsigned long long total = 0;
 	BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
 	if (total >> 62)

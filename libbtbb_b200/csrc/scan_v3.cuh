@@ -71,6 +71,11 @@ struct xparams {
 	int64_t max_hits;
 	unsigned long long *count;
 	int64_t bias;
+	/* slab mode (find_ac_dev): every warp appends to its own slab, so that one sort per
+	 * slab + concatenation in warp order gives the ascending list without a global sort */
+	btbb_b200_hit *slab;
+	uint32_t *slab_cnt;
+	uint32_t slab_cap;
 };
 
 __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t r[8])

@@ -156,6 +156,16 @@ __device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo,
 	}
 	if ((int)e > xp->kmax) return;
 	const uint32_t lap = (uint32_t)(sw >> 34) & 0xffffffu;
+	if (xp->slab_cnt) {          /* slab mode: this warp's own slab (see find_ac.cu) */
+		const uint32_t gw = blockIdx.x * WARPS + (threadIdx.x >> 5), cap = xp->slab_cap;
+		const uint32_t i = atomicAdd(&xp->slab_cnt[gw], 1u);
+		if (i < cap) {
+			btbb_b200_hit h;
+			h.offset = pos + xp->bias; h.lap = lap; h.ac_errors = (uint8_t)e; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+			xp->slab[(size_t)gw * cap + i] = h;
+		}
+		return;
+	}
 	const int64_t max_hits = xp->max_hits;
 	if (max_hits < 0) {          /* first-hit mode, see push_hit() */
 		atomicMin(xp->count, ((unsigned long long)(pos + xp->bias) << 32) | ((unsigned long long)lap << 8) | e);
