@@ -208,10 +208,10 @@ def main():
         cnt, rc = ctx.find_ac_dev(d_stream.data_ptr(), n, d_hits.data_ptr(), cap, lap=B.LAP_ANY, k=K_ERRORS, stream=st)
         assert rc == 0
         if world > 1:
-            mine = d_hits[:cnt].clone()
-            mine.view(torch.int64)[:, 0] += begin          # global offsets
-            allh, counts = sharding.gather_hits(mine)
-            return cnt, int(allh.shape[0])
+            mine = d_hits[:cnt]
+            mine.view(torch.int64)[:, 0] += begin          # global offsets (the buffer is rewritten every step)
+            _, counts = sharding.gather_hits(mine, concat=False)
+            return cnt, int(sum(counts))
         return cnt, cnt
 
     def barrier():

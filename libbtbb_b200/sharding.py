@@ -24,24 +24,36 @@ def shard_read_span(n_positions, rank, world, total_symbols):
     return b, min(total_symbols, e + SEAM)
 
 
-def gather_hits(local_hits, group=None):
+_bufs = {}
+
+
+def gather_hits(local_hits, group=None, concat=True):
     """allgatherv of 16-byte hit records.
 
     local_hits: uint8 tensor [n_local, 16] (device tensor with NCCL, CPU tensor with gloo)
-    whose offsets are already global.  Returns (all_hits [n_total, 16], counts list).
-    NCCL has no native allgatherv: one all_gather of the counts, then one all_gather of
-    the records padded to the largest count.
+    whose offsets are already global.  Returns (all_hits [n_total, 16], counts list); with
+    concat=False the first item is the padded [world, cap, 16] receive buffer instead (rank
+    r's records are buf[r, :counts[r]]), which skips one device copy.
+    NCCL has no native allgatherv: one all_gather of the counts, then one all_gather of the
+    records padded to the largest count.  Buffers are cached between calls.
     """
     world = dist.get_world_size(group)
     dev = local_hits.device
     n_local = torch.tensor([local_hits.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
+    all_n = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_n, n_local, group=group)
+    counts = all_n.tolist()                        # the one host sync of the exchange
     cap = max(max(counts), 1)
-    padded = torch.zeros((cap, 16), dtype=torch.uint8, device=dev)
-    padded[: local_hits.shape[0]] = local_hits
-    bufs = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bufs, padded, group=group)
-    out = torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    cap = (cap + 65535) // 65536 * 65536           # round up so that the buffers get reused
+    key = (str(dev), world, cap)
+    if key not in _bufs:
+        _bufs.clear()
+        _bufs[key] = (torch.zeros((cap, 16), dtype=torch.uint8, device=dev),
+                      torch.empty((world, cap, 16), dtype=torch.uint8, device=dev))
+    send, recv = _bufs[key]
+    send[: local_hits.shape[0]].copy_(local_hits)
+    dist.all_gather_into_tensor(recv.view(world * cap, 16), send, group=group)
+    if not concat:
+        return recv, counts
+    out = torch.cat([recv[r, :c] for r, c in enumerate(counts)], dim=0)
     return out, counts
