@@ -388,6 +388,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 
 #include "scan_v3.cuh"
 #include "scan_v4.cuh"
+#include "scan_known.cuh"
 
 }  // namespace
 
@@ -469,7 +470,8 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	const char *env = getenv("BTBB_B200_SCAN");
 	const bool force_v1 = env && !strcmp(env, "v1");
 	if (n <= 0) return BTBB_B200_OK;
-	if (lap != BTBB_B200_LAP_ANY || !ctx->d_map2 || force_v1)
+	const bool known = lap != BTBB_B200_LAP_ANY;
+	if ((!known && !ctx->d_map2) || force_v1 || (known && k > 16))
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	const int64_t head = (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);
 	int64_t nstrips = n > head ? (n - head) / v3::STRIP : 0;
@@ -503,7 +505,30 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	static_assert(sizeof(v3::xparams) <= 128, "xparams slot");
 	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
 	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
-	if (env && !strcmp(env, "v3")) {
+	if (known) {
+		/* known LAP: bit-sliced prefilter on 16 sync-word bits that are all 0 (or all 1) */
+		vk::args a;
+		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
+		a.ac = bt_gen_syncword(lap); a.lap = lap; a.kmax = k;
+		a.kk = k < 0 ? -1 : (k > 16 ? 16 : k);
+		a.xp = (const v3::xparams *)slot;
+		/* each 32-bit half of the sync word has at least 16 zeros or 16 ones */
+		const uint32_t lo = (uint32_t)a.ac, hi = (uint32_t)(a.ac >> 32);
+		const bool inv = __builtin_popcount(lo) > 16, inv2 = __builtin_popcount(hi) > 16;
+		int cnt = 0;
+		for (int j = 0; j < 32 && cnt < 16; j++)
+			if (((lo >> j) & 1u) == (inv ? 1u : 0u)) a.sh[cnt++] = (uint32_t)j;
+		cnt = 0;
+		for (int j = 0; j < 32 && cnt < 16; j++)
+			if (((hi >> j) & 1u) == (inv2 ? 1u : 0u)) a.sh2[cnt++] = (uint32_t)j;
+		const bool two = k >= 3;
+		if (two && a.kk > 16) a.kk = 16;
+		void (*kern)(const vk::args);
+		if (!two) kern = inv ? vk::scan_known_v4<true, false, false> : vk::scan_known_v4<false, false, false>;
+		else if (inv) kern = inv2 ? vk::scan_known_v4<true, true, true> : vk::scan_known_v4<true, true, false>;
+		else kern = inv2 ? vk::scan_known_v4<false, true, true> : vk::scan_known_v4<false, true, false>;
+		kern<<<(unsigned)grid, vk::WARPS * 32, vk::SMEM_BYTES, st>>>(a);
+	} else if (env && !strcmp(env, "v3")) {
 		v3::args a;
 		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
 		a.lut = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
