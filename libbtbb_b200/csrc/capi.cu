@@ -66,6 +66,7 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_tmp2) cudaFree(ctx->d_tmp2);
 	if (ctx->d_sort_hist) cudaFree(ctx->d_sort_hist);
 	if (ctx->d_xp) cudaFree(ctx->d_xp);
+	if (ctx->d_dbg) cudaFree(ctx->d_dbg);
 	if (ctx->d_slab) cudaFree(ctx->d_slab);
 	if (ctx->d_slab_cnt) cudaFree(ctx->d_slab_cnt);
 	if (ctx->d_slab_base) cudaFree(ctx->d_slab_base);

@@ -34,6 +34,11 @@ struct btbb_b200_ctx {
 	uint32_t *d_map2;            /* bulk kernel: 2^19-bit map of reachable low-32 syndromes, both tails (k <= 2) */
 	uint64_t cc[2];              /* 34-bit syndrome of PN ^ (legal tail << 57) */
 	uint32_t m32, m33;           /* parity masks over codeword bits 32..56 for syndrome bits 32 / 33 */
+	uint32_t m0;                 /* same for syndrome bit 0 */
+	uint32_t *d_dbg;             /* developer counters (BTBB_B200_DBG=1) */
+	int dbg_n;
+	uint32_t *d_lut6;            /* bulk kernel v6: byte tables over codeword bits 41..48 / 49..56 / 33..40 -> syndrome bits 1..32 */
+	uint32_t *d_map6;            /* bulk kernel v6: 2^19-bit + 2^17-bit maps over syndrome bits 1..32 */
 	btbb_b200_hit *d_slab;       /* slab ordering: (warps + 2) x BT_SLAB_CAP records */
 	uint32_t *d_slab_cnt;        /* per-slab fill counts (+ two 64-bit edge counters) */
 	unsigned long long *d_slab_base;

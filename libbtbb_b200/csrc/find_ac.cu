@@ -388,6 +388,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 
 #include "scan_v3.cuh"
 #include "scan_v4.cuh"
+#include "scan_v6.cuh"
 #include "scan_known.cuh"
 
 }  // namespace
@@ -473,8 +474,15 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	const bool known = lap != BTBB_B200_LAP_ANY;
 	if ((!known && !ctx->d_map2) || force_v1 || (known && k > 16))
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
-	const int64_t head = (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);
-	int64_t nstrips = n > head ? (n - head) / v3::STRIP : 0;
+	/* promiscuous default: scan_v4.cuh (LUTMODE 2, five in-place slots).  BTBB_B200_SCAN=v6..
+	 * selects the experimental scan_v6.cuh, whose windows start one symbol before the aligned
+	 * data it loads (so it wants at least one symbol in front); v3 / v4a.. the older variants */
+	const bool use_v6 = !known && env && !strncmp(env, "v6", 2);
+	int64_t al = (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
+	if (use_v6 && al == 0) al = 32;
+	const int64_t head = use_v6 ? al - 1 : al;                                             /* first window of the bulk kernel */
+	/* a strip reads 64 symbols past its end and the stream holds n + 63 */
+	int64_t nstrips = n - 1 > al ? (n - 1 - al) / v3::STRIP : 0;
 	/* the bulk kernels carry 32-bit positions relative to a warp's run: keep a launch below
 	 * 2^31 symbols per warp (148 x 32 warps -> ~10^13 symbols); beyond that the tail kernel
 	 * below simply takes the rest */
@@ -485,20 +493,27 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	v3::xparams xp;
 	memset(&xp, 0, sizeof(xp));
 	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
-	xp.m32 = ctx->m32; xp.m33 = ctx->m33;
+	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0; xp.stream = d_stream;
 	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err;
 	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
+	int bulk_warps = 32;
+	if (use_v6 && env && !strncmp(env, "v6w24", 5)) bulk_warps = 24;
+	else if (use_v6 && env && !strncmp(env, "v6w16", 5)) bulk_warps = 16;
 	int64_t grid = ctx->sm_count;
-	const int64_t need = (nstrips + v3::WARPS - 1) / v3::WARPS;
+	const int64_t need = (nstrips + bulk_warps - 1) / bulk_warps;
 	if (grid > need) grid = need;
 	const bool slab_mode = slab && !(env && !strcmp(env, "v3")) && !(env && !strcmp(env, "noslab"));
 	if (slab_mode) {
-		const int nw = (int)grid * v4::WARPS;
+		const int nw = (int)grid * bulk_warps;
 		int rc2 = bt_ensure_slab(ctx, nw + 2);
 		if (rc2) return rc2;
 		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_slab_cnt, 0, (size_t)(nw + 2) * sizeof(uint32_t) + 2 * sizeof(unsigned long long), st));
 		xp.slab = ctx->d_slab; xp.slab_cnt = ctx->d_slab_cnt; xp.slab_cap = BT_SLAB_CAP;
 		slab->used = 1; slab->nw = nw;
+	}
+	if (getenv("BTBB_B200_DBG")) {
+		if (!ctx->d_dbg) BT_CUDA_TRY(cudaMalloc(&ctx->d_dbg, 148 * 32 * 32));
+		xp.dbg = ctx->d_dbg; ctx->dbg_n = (int)grid * bulk_warps;
 	}
 	if (!ctx->d_xp)
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_xp, 16 * 128));
@@ -508,7 +523,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	if (known) {
 		/* known LAP: bit-sliced prefilter on 16 sync-word bits that are all 0 (or all 1) */
 		vk::args a;
-		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
+		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.ac = bt_gen_syncword(lap); a.lap = lap; a.kmax = k;
 		a.kk = k < 0 ? -1 : (k > 16 ? 16 : k);
 		a.xp = (const v3::xparams *)slot;
@@ -528,15 +543,27 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		else if (inv) kern = inv2 ? vk::scan_known_v4<true, true, true> : vk::scan_known_v4<true, true, false>;
 		else kern = inv2 ? vk::scan_known_v4<false, true, true> : vk::scan_known_v4<false, true, false>;
 		kern<<<(unsigned)grid, vk::WARPS * 32, vk::SMEM_BYTES, st>>>(a);
+	} else if (use_v6) {
+		v6::args a;
+		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
+		a.lut = ctx->d_lut6; a.map = ctx->d_map6; a.xp = (const v3::xparams *)slot;
+		void (*kern)(const v6::args) = v6::scan_promisc_v6<5, 32>;
+		if (env && !strcmp(env, "v6s4")) kern = v6::scan_promisc_v6<4, 32>;
+		else if (env && !strcmp(env, "v6s6")) kern = v6::scan_promisc_v6<6, 32>;
+		else if (env && !strcmp(env, "v6w24")) kern = v6::scan_promisc_v6<5, 24>;
+		else if (env && !strcmp(env, "v6w16")) kern = v6::scan_promisc_v6<5, 16>;
+		else if (env && !strcmp(env, "v6w24s4")) kern = v6::scan_promisc_v6<4, 24>;
+		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v6::SMEM_BYTES));
+		kern<<<(unsigned)grid, bulk_warps * 32, v6::SMEM_BYTES, st>>>(a);
 	} else if (env && !strcmp(env, "v3")) {
 		v3::args a;
-		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
+		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.lut = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
 		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
 		v3::scan_promisc_v3<<<(unsigned)grid, v3::WARPS * 32, v3::SMEM_BYTES, st>>>(a);
 	} else {
 		v4::args a;
-		a.base = d_stream + head; a.pos0 = head; a.nstrips = nstrips;
+		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.lut = ctx->d_lut4; a.lut2 = ctx->d_lut2b; a.lut3 = ctx->d_lut3; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
 		/* experiment switch (developer): v4a..v4f pick LUT mode / inline slots / branch-free slots */
 		void (*kern)(const v4::args) = v4::scan_promisc_v4<2, 5, true>;
@@ -833,4 +860,13 @@ extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream
 	if ((int64_t)total > max_hits)
 		return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
 	return BTBB_B200_OK;
+}
+
+/* developer: copy the per-warp counters of the last bulk launch (BTBB_B200_DBG=1) */
+extern "C" int bt_dbg_read(btbb_b200_ctx *ctx, uint32_t *out, int max_warps)
+{
+	if (!ctx || !ctx->d_dbg) return 0;
+	int n = ctx->dbg_n < max_warps ? ctx->dbg_n : max_warps;
+	if (cudaMemcpy(out, ctx->d_dbg, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	return n;
 }

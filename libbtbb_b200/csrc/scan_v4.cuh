@@ -52,18 +52,23 @@ constexpr uint32_t SA_MAP = 0x10000, SA_WARP = 0x20000;
 constexpr uint32_t S_BYTES = (SW + 8) * 4;
 constexpr uint32_t WARP_BYTES = S_BYTES + QCAP * 2;
 constexpr uint32_t SA_END = SA_WARP + WARPS * WARP_BYTES;
-constexpr size_t SMEM_BYTES = SA_END;
+constexpr size_t SMEM_BYTES = SA_END + (1 << 12) * 4;
 /* LUTMODE 2: three lane-private field tables over codeword bits 34..41 / 42..49 / 50..56
  * (256 + 256 + 128 entries x 128 B = 80 KiB): T0 at 0x4000, T2 at 0xC000, T1 behind the map
  * at 0x20000; the per-warp blocks move to 0x28000 and the overflow queue shrinks to 512. */
 constexpr uint32_t SA_F0 = 0x4000, SA_F2 = 0xC000, SA_F1 = 0x20000, SA_WARP_M2 = 0x28000;
 constexpr int QCAP_M2 = 512;
+/* second-level map: 2^17 bits over syndrome bits 5..21, looked at only after a positive in the
+ * first map (which is 0.7 % full, i.e. ~3.5 false positives per warp and strip): it removes
+ * 97 % of them before they reach the exact queue */
+constexpr int M2_WORDS = 1 << 12;
 constexpr int LUT3_ENTRIES = 256 + 256 + 128;
 template <int LUTMODE> struct layout {
 	static constexpr uint32_t sa_warp = LUTMODE == 2 ? SA_WARP_M2 : SA_WARP;
 	static constexpr int qcap = LUTMODE == 2 ? QCAP_M2 : QCAP;
 	static constexpr uint32_t warp_bytes = S_BYTES + qcap * 2;
-	static constexpr size_t smem_bytes = sa_warp + WARPS * warp_bytes;
+	static constexpr uint32_t sa_m2 = sa_warp + WARPS * warp_bytes;       /* second-level map */
+	static constexpr size_t smem_bytes = sa_m2 + M2_WORDS * 4;
 };
 
 struct args {
@@ -73,7 +78,7 @@ struct args {
 	const uint32_t *lut;     /* LUT_ENTRIES words: the four field tables back to back (LUTMODE 0) */
 	const uint32_t *lut3;    /* LUT3_ENTRIES words: three field tables (LUTMODE 2) */
 	const uint32_t *lut2;    /* LUT A (2^13 entries, codeword bits 34..46) then LUT B (2^10, bits 47..56) (LUTMODE 1) */
-	const uint32_t *map;     /* MAP_WORDS */
+	const uint32_t *map;     /* MAP_WORDS, then M2_WORDS of the second-level map */
 	const xparams *xp;
 };
 
@@ -126,15 +131,20 @@ __device__ __forceinline__ uint32_t map_bit(uint32_t sy)
 	return (mw >> (sy & 31)) & 1;
 }
 
-/* exact test needs the 2-LUT-free syndrome too: reuse the lane-private tables */
-template <int LUTMODE>
-__device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo, uint32_t hi)
+template <uint32_t SA_M2>
+__device__ __forceinline__ uint32_t map2_bit(uint32_t sy)
 {
-	const uint32_t lane4 = (threadIdx.x & 31) * 4;
+	const uint32_t mw = lds32o<SA_M2>((sy >> 8) & (uint32_t)((M2_WORDS - 1) * 4));
+	return (mw >> ((sy >> 5) & 31)) & 1;
+}
+
+/* Second half of the reference's decision (bluetooth_packet.c:387-416) for a window whose
+ * 34-bit syndrome of the received part is known: fold in the tail constant, look the error
+ * pattern up, count, extract the LAP, emit. */
+__device__ __noinline__ void exact_tail(const xparams *xp, int64_t pos, uint32_t lo, uint32_t hi, uint64_t syn)
+{
 	const uint32_t tail = hi >> 25;
 	const int cls = __popc((tail ^ BT_BARKER_A) & 0x7f) <= 3 ? 0 : 1;
-	uint64_t syn = (uint64_t)syn32<LUTMODE>(lo, hi, lane4) | ((uint64_t)(__popc(hi & xp->m32) & 1) << 32) |
-		       ((uint64_t)(__popc(hi & xp->m33) & 1) << 33);
 	syn ^= xp->cc[cls];
 	uint64_t sw = (((uint64_t)hi << 32) | lo) & 0x01ffffffffffffffULL;
 	sw |= (uint64_t)(cls ? BT_BARKER_B : BT_BARKER_A) << 57;
@@ -157,7 +167,7 @@ __device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo,
 	if ((int)e > xp->kmax) return;
 	const uint32_t lap = (uint32_t)(sw >> 34) & 0xffffffu;
 	if (xp->slab_cnt) {          /* slab mode: this warp's own slab (see find_ac.cu) */
-		const uint32_t gw = blockIdx.x * WARPS + (threadIdx.x >> 5), cap = xp->slab_cap;
+		const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), cap = xp->slab_cap;
 		const uint32_t i = atomicAdd(&xp->slab_cnt[gw], 1u);
 		if (i < cap) {
 			btbb_b200_hit h;
@@ -177,6 +187,16 @@ __device__ __noinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo,
 		h.offset = pos + xp->bias; h.lap = lap; h.ac_errors = (uint8_t)e; h.pad[0] = h.pad[1] = h.pad[2] = 0;
 		xp->hits[slot] = h;
 	}
+}
+
+/* exact test: the low 32 syndrome bits come from the same tables as the filter's */
+template <int LUTMODE>
+__device__ __forceinline__ void exact4(const xparams *xp, int64_t pos, uint32_t lo, uint32_t hi)
+{
+	const uint32_t lane4 = (threadIdx.x & 31) * 4;
+	const uint64_t syn = (uint64_t)syn32<LUTMODE>(lo, hi, lane4) | ((uint64_t)(__popc(hi & xp->m32) & 1) << 32) |
+			     ((uint64_t)(__popc(hi & xp->m33) & 1) << 33);
+	exact_tail(xp, pos, lo, hi, syn);
 }
 
 template <int LUTMODE>
@@ -229,7 +249,8 @@ __device__ __forceinline__ void slot(uint32_t &c, uint32_t &hitm, uint32_t w0, u
 		const uint32_t q = bfind(c);
 		c ^= 1u << q;
 		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
-		if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
+		const uint32_t sy = syn32<LUTMODE>(lo, hi, lane4);
+		if (map_bit(sy) && map2_bit<layout<LUTMODE>::sa_m2>(sy))
 			park4<LUTMODE>(xp, x_sa, word_pos + q, lo, hi);
 	}
 }
@@ -242,7 +263,9 @@ __device__ __forceinline__ void park_row(uint32_t hitm, uint32_t w0, uint32_t w1
 	while (hitm) {
 		const uint32_t q = bfind(hitm);
 		hitm ^= 1u << q;
-		park4<LUTMODE>(xp, x_sa, word_pos + q, __funnelshift_r(w0, w1, q), __funnelshift_r(w1, w2, q));
+		const uint32_t lo = __funnelshift_r(w0, w1, q), hi = __funnelshift_r(w1, w2, q);
+		if (map2_bit<layout<LUTMODE>::sa_m2>(syn32<LUTMODE>(lo, hi, (threadIdx.x & 31) * 4)))
+			park4<LUTMODE>(xp, x_sa, word_pos + q, lo, hi);
 	}
 }
 
@@ -274,6 +297,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		for (int i = threadIdx.x; i < 1024; i += WARPS * 32) sts32(0x4000 + 4 * i, a.lut2[8192 + i]);
 	}
 	for (int i = threadIdx.x; i < MAP_WORDS; i += WARPS * 32) sts32(SA_MAP + 4 * i, a.map[i]);
+	for (int i = threadIdx.x; i < M2_WORDS; i += WARPS * 32) sts32(layout<LUTMODE>::sa_m2 + 4 * i, a.map[MAP_WORDS + i]);
 	const uint32_t x_sa = SA_X + wid * X_BYTES;
 	const uint32_t s_sa = layout<LUTMODE>::sa_warp + wid * layout<LUTMODE>::warp_bytes;
 	const uint32_t q_sa = s_sa + S_BYTES;
@@ -287,6 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 	}
 	__syncthreads();
 	const uint32_t lane4 = 4 * lane, my_sa = s_sa + lane4;
+	const long long dbg_t0 = clock64();
 
 	for (int64_t s = s_begin; s < s_end; s++) {
 		uint32_t wv[K];
@@ -369,7 +394,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 					const uint32_t wa = s_sa + (e >> 5);
 					const uint32_t w0 = lds32o<0>(wa), x1 = lds32o<4>(wa), x2 = lds32o<8>(wa);
 					const uint32_t lo = __funnelshift_r(w0, x1, e), hi = __funnelshift_r(x1, x2, e);
-					if (map_bit(syn32<LUTMODE>(lo, hi, lane4)))
+					const uint32_t sy = syn32<LUTMODE>(lo, hi, lane4);
+					if (map_bit(sy) && map2_bit<layout<LUTMODE>::sa_m2>(sy))
 						park4<LUTMODE>(xp, x_sa, strip_pos + (e >> 7) * 32 + (e & 31), lo, hi);
 				}
 				__syncwarp();
@@ -380,6 +406,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		if (lds32(x_sa) >= XCAP / 2) flush4<LUTMODE>(xp, x_sa, lane);
 	}
 	flush4<LUTMODE>(xp, x_sa, lane);
+	if (xp->dbg && lane == 0) {
+		for (int j = 0; j < 8; j++) xp->dbg[8 * gw + j] = 0;
+		xp->dbg[8 * gw + 2] = (uint32_t)(clock64() - dbg_t0); xp->dbg[8 * gw + 3] = (uint32_t)(s_end - s_begin);
+	}
 }
 
 }  // namespace v4
