@@ -104,6 +104,21 @@ int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t s
 			  btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits,
 			  void *cuda_stream);
 
+/*
+ * btbb_b200_find_ac_dev for a stream that is already PACKED, 32 symbols per word: symbol i of
+ * the stream is bit (i & 31) of d_words[i >> 5] -- the reference's own bit order when it packs
+ * a window (air_to_host64, bluetooth_packet.c:235-242: symbol i <-> bit i).  This is the
+ * packed-symbol ingest of SURVEY.md 8(f) row 2: a producer that keeps demodulated bits packed
+ * skips the 8x byte-per-symbol inflation.  d_words must be 4-byte aligned and hold
+ * ceil((search_length + 63) / 32) words.  Same results, ordering and error behaviour as
+ * btbb_b200_find_ac_dev.  (btbb_b200_find_ac_host uses this path internally for large
+ * buffers: it packs on the host cores while copying, because PCIe is the bound there.)
+ */
+int btbb_b200_find_ac_packed_dev(btbb_b200_ctx *ctx, const uint32_t *d_words, int64_t search_length,
+				 uint32_t lap, int max_ac_errors,
+				 btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits,
+				 void *cuda_stream);
+
 /* Same, but only enqueues the scan kernel(s) (no synchronisation, no ordering pass);
  * used by the benchmark to time the kernel alone.  d_count is a device int64 counter
  * of the hits (unordered), zeroed by the call itself on the same stream. */

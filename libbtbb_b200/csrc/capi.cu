@@ -6,6 +6,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <emmintrin.h>
+#include <pthread.h>
+#include <sched.h>
+#include <atomic>
+#include <thread>
+#include <vector>
 #include "capi_internal.h"
 
 static __thread char g_err[256] = "";
@@ -67,6 +73,9 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_sort_hist) cudaFree(ctx->d_sort_hist);
 	if (ctx->d_xp) cudaFree(ctx->d_xp);
 	if (ctx->d_dbg) cudaFree(ctx->d_dbg);
+	if (ctx->d_unpack) cudaFree(ctx->d_unpack);
+	if (ctx->d_packed) cudaFree(ctx->d_packed);
+	for (int i = 0; i < 2; i++) if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
 	if (ctx->d_slab) cudaFree(ctx->d_slab);
 	if (ctx->d_slab_cnt) cudaFree(ctx->d_slab_cnt);
 	if (ctx->d_slab_base) cudaFree(ctx->d_slab_base);
@@ -154,6 +163,173 @@ static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_leng
 	return BTBB_B200_OK;
 }
 
+/* ---------------- host pack stage ----------------
+ * The reference hands symbols over one per char (btbb.h:82-94); over PCIe that is 8 bits of
+ * traffic per bit of information and the copy, not the scan, bounds a host-buffer call.  Large
+ * calls therefore pack 32 symbols per word on the host (all cores, SSE2 movemask), copy the
+ * packed words chunk by chunk while the next chunk is being packed, and run the packed
+ * variants of the bulk kernels.  This is a change of transfer format only: every decision is
+ * still made on the device. */
+namespace {
+
+inline uint32_t pack32_host(const char *p)
+{
+	const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
+	const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p + 16));
+	return (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(a, 7)) | ((uint32_t)_mm_movemask_epi8(_mm_slli_epi16(b, 7)) << 16);
+}
+
+/* symbols [first, first + 32 * nwords) -> out[0 .. nwords), never reading at or past `limit` */
+void pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out)
+{
+	int64_t w = 0;
+	for (; w < nwords && first + 32 * (w + 1) <= limit; w++) out[w] = pack32_host(stream + first + 32 * w);
+	for (; w < nwords; w++) {
+		uint32_t v = 0;
+		for (int j = 0; j < 32 && first + 32 * w + j < limit; j++) v |= (uint32_t)(stream[first + 32 * w + j] & 1) << j;
+		out[w] = v;
+	}
+}
+
+struct pack_job {
+	const char *stream;
+	int64_t limit;              /* readable symbols */
+	int64_t chunk_words, nchunks, total_words;
+	uint32_t *stage[2];
+	int nthreads;
+	std::atomic<int> ready;     /* 0: workers wait, 1: barriers are set up, -1: give up */
+	std::atomic<int64_t> next;  /* next block of the current chunk (blocks are handed out dynamically) */
+	pthread_barrier_t start, done;
+};
+
+struct pack_arg { pack_job *job; int tid; };
+
+void *pack_worker(void *p)
+{
+	pack_arg *pa = static_cast<pack_arg *>(p);
+	pack_job *j = pa->job;
+	int r;
+	while ((r = j->ready.load(std::memory_order_acquire)) == 0) sched_yield();
+	if (r < 0) return NULL;
+	for (int64_t c = 0; c < j->nchunks; c++) {
+		pthread_barrier_wait(&j->start);
+		const int64_t w0 = c * j->chunk_words;
+		const int64_t nw = j->total_words - w0 < j->chunk_words ? j->total_words - w0 : j->chunk_words;
+		const int64_t BLOCK = 16384;     /* words: 512 Ki symbols per grab */
+		for (;;) {
+			const int64_t a = j->next.fetch_add(BLOCK, std::memory_order_relaxed);
+			if (a >= nw) break;
+			const int64_t b = a + BLOCK < nw ? a + BLOCK : nw;
+			pack_range(j->stream, 32 * (w0 + a), b - a, j->limit, j->stage[c & 1] + a);
+		}
+		pthread_barrier_wait(&j->done);
+	}
+	return NULL;
+}
+
+}  // namespace
+
+/* stream[0 .. nsym) -> ctx->d_packed (ceil(nsym / 32) words), copies issued on copy_stream[0] */
+static int pack_and_upload(btbb_b200_ctx *ctx, const char *stream, int64_t nsym)
+{
+	const int64_t total_words = (nsym + 31) / 32;
+	const int64_t CHUNK_WORDS = (int64_t)8 << 20;      /* 256 Mi symbols -> 32 MiB packed */
+	for (int i = 0; i < 2; i++)
+		if (!ctx->copy_stream[i])
+			BT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
+	if (total_words + 2 > ctx->packed_cap) {
+		if (ctx->d_packed) cudaFree(ctx->d_packed);
+		ctx->d_packed = NULL; ctx->packed_cap = 0;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_packed, (size_t)(total_words + 2) * sizeof(uint32_t)));
+		ctx->packed_cap = total_words + 2;
+	}
+	const int64_t chunk_words = total_words < CHUNK_WORDS ? total_words : CHUNK_WORDS;
+	if (chunk_words > ctx->h_pack_cap) {
+		for (int i = 0; i < 2; i++) {
+			if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
+			ctx->h_pack[i] = NULL;
+		}
+		ctx->h_pack_cap = 0;
+		for (int i = 0; i < 2; i++)
+			BT_CUDA_TRY(cudaMallocHost(&ctx->h_pack[i], (size_t)chunk_words * sizeof(uint32_t)));
+		ctx->h_pack_cap = chunk_words;
+	}
+	pack_job job;
+	job.stream = stream; job.limit = nsym;
+	job.chunk_words = chunk_words; job.total_words = total_words;
+	job.nchunks = (total_words + chunk_words - 1) / chunk_words;
+	job.stage[0] = ctx->h_pack[0]; job.stage[1] = ctx->h_pack[1];
+	/* measured on a 2 x 32-core host (profiles/README.md): 16 threads already pack faster than
+	 * PCIe copies the bytes would take; more threads gain little and get unstable under a CPU quota */
+	int nt = (int)std::thread::hardware_concurrency();
+	if (nt > 16) nt = 16;
+	if (const char *e = getenv("BTBB_B200_PACK_THREADS")) nt = atoi(e);
+	if (nt < 1) nt = 1;
+	if (nt > 128) nt = 128;
+	if ((int64_t)nt > (chunk_words + 65535) / 65536) nt = (int)((chunk_words + 65535) / 65536);
+	job.ready.store(0);
+	std::vector<pthread_t> th((size_t)nt);
+	std::vector<pack_arg> args((size_t)nt);
+	int started = 0;
+	for (; started < nt; started++) {
+		args[(size_t)started].job = &job; args[(size_t)started].tid = started;
+		if (pthread_create(&th[(size_t)started], NULL, pack_worker, &args[(size_t)started])) break;
+	}
+	if (started == 0)
+		return btbb_b200_set_error(BTBB_B200_ENOMEM, "find_ac_host: cannot start pack threads");
+	nt = started;                 /* fewer threads than asked for is fine */
+	job.nthreads = nt;
+	pthread_barrier_init(&job.start, NULL, (unsigned)nt + 1);
+	pthread_barrier_init(&job.done, NULL, (unsigned)nt + 1);
+	job.ready.store(1, std::memory_order_release);
+	cudaEvent_t ev[2] = {NULL, NULL};
+	cudaError_t e = cudaSuccess;
+	for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+	for (int64_t c = 0; c < job.nchunks; c++) {
+		/* the staging buffer of chunk c was last used by the copy of chunk c - 2 */
+		if (c >= 2 && e == cudaSuccess) e = cudaEventSynchronize(ev[c & 1]);
+		job.next.store(0, std::memory_order_relaxed);
+		pthread_barrier_wait(&job.start);
+		pthread_barrier_wait(&job.done);
+		const int64_t w0 = c * chunk_words;
+		const int64_t nw = total_words - w0 < chunk_words ? total_words - w0 : chunk_words;
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(ctx->d_packed + w0, job.stage[c & 1], (size_t)nw * sizeof(uint32_t),
+					    cudaMemcpyHostToDevice, ctx->copy_stream[0]);
+		if (e == cudaSuccess) e = cudaEventRecord(ev[c & 1], ctx->copy_stream[0]);
+	}
+	for (int i = 0; i < nt; i++) pthread_join(th[(size_t)i], NULL);
+	pthread_barrier_destroy(&job.start); pthread_barrier_destroy(&job.done);
+	for (int i = 0; i < 2; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+	if (e != cudaSuccess) return btbb_b200_cuda_fail(e, "find_ac_host: packed upload");
+	return BTBB_B200_OK;
+}
+
+/* large host-buffer call: pack, upload, scan the packed stream, bring the ordered hits back */
+static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t search_length, uint32_t lap,
+			    int max_ac_errors, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits)
+{
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	int rc = pack_and_upload(ctx, stream, search_length + 63);
+	if (rc) return rc;
+	const int64_t cap = max_hits > 0 ? max_hits : 1;
+	if (cap > ctx->tmp2_cap) {
+		if (ctx->d_tmp2) cudaFree(ctx->d_tmp2);
+		ctx->d_tmp2 = NULL; ctx->tmp2_cap = 0;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_tmp2, (size_t)cap * sizeof(btbb_b200_hit)));
+		ctx->tmp2_cap = cap;
+	}
+	cudaStream_t st = ctx->copy_stream[0];
+	rc = bt_find_ac_dev_impl(ctx, reinterpret_cast<const uint8_t *>(ctx->d_packed), 1, search_length, lap,
+				 max_ac_errors, ctx->d_tmp2, max_hits, n_hits, st);
+	if (rc != BTBB_B200_OK && rc != BTBB_B200_EOVERFLOW) return rc;
+	const int64_t have = *n_hits < max_hits ? *n_hits : max_hits;
+	if (have > 0)
+		BT_CUDA_TRY(cudaMemcpyAsync(hits, ctx->d_tmp2, (size_t)have * sizeof(btbb_b200_hit), cudaMemcpyDeviceToHost, st));
+	BT_CUDA_TRY(cudaStreamSynchronize(st));
+	return rc;
+}
+
 extern "C" int btbb_b200_find_ac_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_length,
 				      uint32_t lap, int max_ac_errors, btbb_b200_hit *hits,
 				      int64_t max_hits, int64_t *n_hits)
@@ -163,6 +339,9 @@ extern "C" int btbb_b200_find_ac_host(btbb_b200_ctx *ctx, const char *stream, in
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_host: bad arguments");
 	*n_hits = 0;
 	if (search_length == 0) return BTBB_B200_OK;
+	const char *env = getenv("BTBB_B200_HOST");      /* developer: "bytes" keeps the byte-format copy */
+	if (search_length >= ((int64_t)4 << 20) && !(env && !strcmp(env, "bytes")))
+		return scan_host_packed(ctx, stream, search_length, lap, max_ac_errors, hits, max_hits, n_hits);
 	return scan_host(ctx, stream, search_length, lap, max_ac_errors, hits, max_hits, n_hits, NULL);
 }
 

@@ -57,6 +57,12 @@ struct btbb_b200_ctx {
 	uint32_t *d_sort_hist;       /* radix-sort histograms */
 	int64_t sort_hist_cap;
 	uint8_t *d_stage[2];         /* device staging for the host-buffer entry points */
+	uint8_t *d_unpack;           /* packed input: bytes of the ragged tail (or of the whole stream when no bulk kernel applies) */
+	int64_t unpack_cap;
+	uint32_t *d_packed;          /* host entry point: the packed stream on the device */
+	int64_t packed_cap;          /* words */
+	uint32_t *h_pack[2];         /* pinned staging for the host pack stage */
+	int64_t h_pack_cap;          /* words each */
 	int64_t stage_cap;
 	cudaStream_t copy_stream[2];
 };
@@ -76,7 +82,9 @@ struct bt_slab_req { int used, nw; };
 int bt_ensure_slab(btbb_b200_ctx *ctx, int nslabs);
 int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		      btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
-		      int64_t bias, cudaStream_t st, bt_slab_req *slab);
+		      int64_t bias, cudaStream_t st, bt_slab_req *slab, int packed = 0);
+int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits, cudaStream_t st);
 int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits);
 int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,

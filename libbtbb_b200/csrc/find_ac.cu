@@ -448,6 +448,34 @@ static int scan_launch_v1(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n
 	return BTBB_B200_OK;
 }
 
+/* ---------------- packed input (format B): expand a range to the byte format ---------------- */
+namespace {
+__global__ void unpack_kernel(const uint32_t *__restrict__ words, int64_t first, int64_t count, uint8_t *__restrict__ out)
+{
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+		const int64_t p = first + i;
+		out[i] = (uint8_t)((words[p >> 5] >> (p & 31)) & 1u);
+	}
+}
+}  // namespace
+
+/* symbols [first, first + count) of a packed stream -> ctx->d_unpack, one byte each */
+static int unpack_to_bytes(btbb_b200_ctx *ctx, const uint32_t *d_words, int64_t first, int64_t count, cudaStream_t st)
+{
+	if (count > ctx->unpack_cap) {
+		if (ctx->d_unpack) cudaFree(ctx->d_unpack);
+		ctx->d_unpack = NULL; ctx->unpack_cap = 0;
+		int64_t cap = count < 16384 ? 16384 : count;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_unpack, (size_t)cap + 64));
+		ctx->unpack_cap = cap;
+	}
+	int64_t blocks = (count + 255) / 256;
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	unpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_words, first, count, ctx->d_unpack);
+	BT_CUDA_TRY(cudaGetLastError());
+	return BTBB_B200_OK;
+}
+
 /*
  * Dispatcher.  The promiscuous scan with tables for k <= 2 runs the warp-autonomous bulk
  * kernel (scan_v4.cuh; BTBB_B200_SCAN=v3 selects its predecessor) over every whole 4096-symbol strip that starts on a 32-byte
@@ -465,20 +493,27 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
  * whether it was taken and how many warps the bulk kernel ran with. */
 int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		      btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
-		      int64_t bias, cudaStream_t st, bt_slab_req *slab)
+		      int64_t bias, cudaStream_t st, bt_slab_req *slab, int packed)
 {
 	if (slab) slab->used = 0;
 	const char *env = getenv("BTBB_B200_SCAN");
 	const bool force_v1 = env && !strcmp(env, "v1");
 	if (n <= 0) return BTBB_B200_OK;
 	const bool known = lap != BTBB_B200_LAP_ANY;
-	if ((!known && !ctx->d_map2) || force_v1 || (known && k > 16))
+	if ((!known && !ctx->d_map2) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
+		if (packed) {      /* no bulk kernel for this case: expand to the byte format and take the tile kernel */
+			int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), 0, n + 63, st);
+			if (rc0) return rc0;
+			d_stream = ctx->d_unpack;
+		}
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
+	}
+	if (packed) env = NULL;      /* the developer switches below are for the byte format */
 	/* promiscuous default: scan_v4.cuh (LUTMODE 2, five in-place slots).  BTBB_B200_SCAN=v6..
 	 * selects the experimental scan_v6.cuh, whose windows start one symbol before the aligned
 	 * data it loads (so it wants at least one symbol in front); v3 / v4a.. the older variants */
-	const bool use_v6 = !known && env && !strncmp(env, "v6", 2);
-	int64_t al = (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
+	const bool use_v6 = !known && !packed && env && !strncmp(env, "v6", 2);
+	int64_t al = packed ? 0 : (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
 	if (use_v6 && al == 0) al = 32;
 	const int64_t head = use_v6 ? al - 1 : al;                                             /* first window of the bulk kernel */
 	/* a strip reads 64 symbols past its end and the stream holds n + 63 */
@@ -487,13 +522,20 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	 * 2^31 symbols per warp (148 x 32 warps -> ~10^13 symbols); beyond that the tail kernel
 	 * below simply takes the rest */
 	if (nstrips > ((int64_t)1 << 31) / v3::STRIP * 4096) nstrips = ((int64_t)1 << 31) / v3::STRIP * 4096;
-	if (nstrips < 1)
+	if (nstrips < 1)      /* (never with packed input: checked above) */
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	const int64_t body_end = head + nstrips * v3::STRIP;
+	/* packed input: the tile kernel takes the ragged tail from an expanded copy */
+	const uint8_t *d_tail = d_stream + body_end;
+	if (packed && body_end < n) {
+		int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), body_end, n - body_end + 63, st);
+		if (rc0) return rc0;
+		d_tail = ctx->d_unpack;
+	}
 	v3::xparams xp;
 	memset(&xp, 0, sizeof(xp));
 	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
-	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0; xp.stream = d_stream;
+	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0; xp.stream = packed ? NULL : d_stream;
 	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err;
 	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
 	int bulk_warps = 32;
@@ -539,9 +581,15 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		const bool two = k >= 3;
 		if (two && a.kk > 16) a.kk = 16;
 		void (*kern)(const vk::args);
-		if (!two) kern = inv ? vk::scan_known_v4<true, false, false> : vk::scan_known_v4<false, false, false>;
-		else if (inv) kern = inv2 ? vk::scan_known_v4<true, true, true> : vk::scan_known_v4<true, true, false>;
-		else kern = inv2 ? vk::scan_known_v4<false, true, true> : vk::scan_known_v4<false, true, false>;
+		if (!packed) {
+			if (!two) kern = inv ? vk::scan_known_v4<true, false, false> : vk::scan_known_v4<false, false, false>;
+			else if (inv) kern = inv2 ? vk::scan_known_v4<true, true, true> : vk::scan_known_v4<true, true, false>;
+			else kern = inv2 ? vk::scan_known_v4<false, true, true> : vk::scan_known_v4<false, true, false>;
+		} else {
+			if (!two) kern = inv ? vk::scan_known_v4<true, false, false, true> : vk::scan_known_v4<false, false, false, true>;
+			else if (inv) kern = inv2 ? vk::scan_known_v4<true, true, true, true> : vk::scan_known_v4<true, true, false, true>;
+			else kern = inv2 ? vk::scan_known_v4<false, true, true, true> : vk::scan_known_v4<false, true, false, true>;
+		}
 		kern<<<(unsigned)grid, vk::WARPS * 32, vk::SMEM_BYTES, st>>>(a);
 	} else if (use_v6) {
 		v6::args a;
@@ -566,7 +614,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.lut = ctx->d_lut4; a.lut2 = ctx->d_lut2b; a.lut3 = ctx->d_lut3; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
 		/* experiment switch (developer): v4a..v4f pick LUT mode / inline slots / branch-free slots */
-		void (*kern)(const v4::args) = v4::scan_promisc_v4<2, 5, true>;
+		void (*kern)(const v4::args) = packed ? v4::scan_promisc_v4<2, 5, true, true> : v4::scan_promisc_v4<2, 5, true>;
 		size_t smem = v4::layout<2>::smem_bytes;
 		if (env && !strncmp(env, "v4", 2) && env[2] >= 'a' && env[2] <= 'f') smem = v4::SMEM_BYTES;
 		if (env && !strcmp(env, "v4a")) kern = v4::scan_promisc_v4<0, 5, false>;
@@ -590,14 +638,14 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		if (head > 0)
 			rc = scan_launch_v1(ctx, d_stream, head, lap, k, ctx->d_slab + (size_t)nw * BT_SLAB_CAP, BT_SLAB_CAP, edge_cnt, bias, st);
 		if (!rc && body_end < n)
-			rc = scan_launch_v1(ctx, d_stream + body_end, n - body_end, lap, k, ctx->d_slab + (size_t)(nw + 1) * BT_SLAB_CAP,
+			rc = scan_launch_v1(ctx, d_tail, n - body_end, lap, k, ctx->d_slab + (size_t)(nw + 1) * BT_SLAB_CAP,
 					    BT_SLAB_CAP, edge_cnt + 1, bias + body_end, st);
 		return rc;
 	}
 	if (head > 0)
 		rc = scan_launch_v1(ctx, d_stream, head, lap, k, d_out, max_hits, d_count, bias, st);
 	if (!rc && body_end < n)
-		rc = scan_launch_v1(ctx, d_stream + body_end, n - body_end, lap, k, d_out, max_hits, d_count, bias + body_end, st);
+		rc = scan_launch_v1(ctx, d_tail, n - body_end, lap, k, d_out, max_hits, d_count, bias + body_end, st);
 	return rc;
 }
 
@@ -789,9 +837,29 @@ extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream
 	if (!ctx || !n_hits || (!d_hits && max_hits > 0) || (!d_stream && search_length > 0) ||
 	    search_length < 0 || max_hits < 0 || (lap != BTBB_B200_LAP_ANY && lap > 0xffffffu))
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: bad arguments");
-	cudaStream_t st = (cudaStream_t)cuda_stream;
+	return bt_find_ac_dev_impl(ctx, d_stream, 0, search_length, lap, max_ac_errors, d_hits, max_hits, n_hits,
+				   (cudaStream_t)cuda_stream);
+}
+
+extern "C" int btbb_b200_find_ac_packed_dev(btbb_b200_ctx *ctx, const uint32_t *d_words, int64_t search_length,
+					    uint32_t lap, int max_ac_errors, btbb_b200_hit *d_hits,
+					    int64_t max_hits, int64_t *n_hits, void *cuda_stream)
+{
+	if (!ctx || !n_hits || (!d_hits && max_hits > 0) || (!d_words && search_length > 0) ||
+	    search_length < 0 || max_hits < 0 || (lap != BTBB_B200_LAP_ANY && lap > 0xffffffu) ||
+	    (reinterpret_cast<uintptr_t>(d_words) & 3))
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_packed: bad arguments");
+	return bt_find_ac_dev_impl(ctx, reinterpret_cast<const uint8_t *>(d_words), 1, search_length, lap, max_ac_errors,
+				   d_hits, max_hits, n_hits, (cudaStream_t)cuda_stream);
+}
+
+/* device-resident stream (bytes, or packed words when `packed`) -> ascending hit list in d_hits */
+int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits, cudaStream_t st)
+{
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
 	*n_hits = 0;
+	if (search_length == 0) return BTBB_B200_OK;
 	int rc = bt_ensure_tmp(ctx, max_hits > 0 ? max_hits : 1);
 	if (rc) return rc;
 	unsigned long long total = 0;
@@ -799,7 +867,7 @@ extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream
 	if (lap == BTBB_B200_LAP_ANY) {
 		bt_slab_req req;
 		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(unsigned long long), st));
-		rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, 0, st, &req);
+		rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, 0, st, &req, packed);
 		if (rc) return rc;
 		if (req.used) {
 			const int nw = req.nw;
@@ -845,7 +913,7 @@ extern "C" int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream
 	btbb_b200_hit *first = (passes & 1) ? ctx->d_tmp : d_hits;
 	btbb_b200_hit *other = (passes & 1) ? d_hits : ctx->d_tmp;
 	BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
-	rc = bt_scan_launch(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, 0, st);
+	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, 0, st, NULL, packed);
 	if (rc) return rc;
 	BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
 	BT_CUDA_TRY(cudaStreamSynchronize(st));

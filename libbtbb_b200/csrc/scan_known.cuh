@@ -19,6 +19,7 @@
 namespace vk {
 
 using v3::ld256;
+using v3::ldg32;
 using v3::lds32;
 using v3::lds32o;
 using v3::sts32;
@@ -100,7 +101,7 @@ __device__ __forceinline__ uint32_t le_const(const uint32_t *cnt, int kk)
 
 /* TWO: a second group of 16 positions in the upper sync-word half (used for k >= 3, where 16
  * positions alone would let through 1 .. 10 % of random windows) */
-template <bool INV, bool TWO, bool INV2>
+template <bool INV, bool TWO, bool INV2, bool PACKED = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_known_v4(const args a)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -118,7 +119,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_known_v4(const args a)
 
 	for (int64_t s = s_begin; s < s_end; s++) {
 		uint32_t wv[K];
-		{
+		if (PACKED) {      /* stream already packed 32 symbols per word (see scan_v4.cuh) */
+			const uint32_t *pw = reinterpret_cast<const uint32_t *>(a.base) + s * (32 * K) + lane;
+			#pragma unroll
+			for (int k = 0; k < K; k++) wv[k] = ldg32(pw + 32 * k);
+			#pragma unroll
+			for (int k = 0; k < K; k++) sts32(my_sa + 128 * k, wv[k]);
+			if (lane < 2) sts32(my_sa + 128 * K, ldg32(pw + 32 * K));
+			if (s + 1 < s_end && lane < K)
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(pw - lane + 32 * K + 32 * lane));
+		} else {
 			uint32_t raw[K][8];
 			const uint8_t *p = a.base + s * STRIP + lane * 32;
 			#pragma unroll

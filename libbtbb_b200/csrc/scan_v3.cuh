@@ -87,6 +87,12 @@ __device__ __forceinline__ void ld256(const uint8_t *p, uint32_t r[8])
 		     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
 		     : "l"(p));
 }
+__device__ __forceinline__ uint32_t ldg32(const uint32_t *p)
+{
+	uint32_t v;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t sa)
 {
 	uint32_t v;

@@ -26,6 +26,7 @@
 namespace v4 {
 
 using v3::ld256;
+using v3::ldg32;
 using v3::lds32;
 using v3::lds32o;
 using v3::lds16o;
@@ -269,7 +270,10 @@ __device__ __forceinline__ void park_row(uint32_t hitm, uint32_t w0, uint32_t w1
 	}
 }
 
-template <int LUTMODE, int NSLOTS, bool BF>
+/* PACKED: a.base points at the stream already packed 32 symbols per word, LSB first (format B
+ * of SURVEY.md 8d; the host entry points pack before the PCIe copy): the load / pack stage
+ * becomes one 4-byte load per lane and row */
+template <int LUTMODE, int NSLOTS, bool BF, bool PACKED = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -316,7 +320,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 	for (int64_t s = s_begin; s < s_end; s++) {
 		uint32_t wv[K];
 		/* ---- load + pack ---- */
-		{
+		if (PACKED) {
+			const uint32_t *pw = reinterpret_cast<const uint32_t *>(a.base) + s * SW + lane;
+			#pragma unroll
+			for (int k = 0; k < K; k++) wv[k] = ldg32(pw + 32 * k);
+			#pragma unroll
+			for (int k = 0; k < K; k++) sts32(my_sa + 128 * k, wv[k]);
+			if (lane < 2) sts32(my_sa + 128 * K, ldg32(pw + SW));
+			if (s + 1 < s_end && lane < K)
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(pw - lane + SW + 32 * lane));
+		} else {
 			uint32_t raw[K][8];
 			const uint8_t *p = a.base + s * STRIP + lane * 32;
 			#pragma unroll

@@ -152,3 +152,54 @@ def test_full_size_10gbit_properties(product_lib):
         h2 = d_hits.cpu().numpy()[: c2 * 16].view(B.HIT_DTYPE).copy()
         h2["offset"] += half
         assert np.concatenate([h1, h2]).tobytes() == hits.tobytes()
+
+
+def _pack_words(s):
+    """format B: symbol i -> bit (i & 31) of word i >> 5 (bluetooth_packet.c:235-242 bit order)"""
+    pad = (-len(s)) % 32
+    b = np.packbits(np.concatenate([s, np.zeros(pad, dtype=np.uint8)]), bitorder="little")
+    return b.view("<u4").copy()
+
+
+@pytest.mark.parametrize("n", [1, 33, 4095, 4096, 4097, 4160, 8192 + 7, 300_001, 2_000_003])
+def test_packed_ingest_matches_oracle(gpu_ctx2, orc, n):
+    """btbb_b200_find_ac_packed_dev == oracle on the same symbols, all bulk / tail / fallback routes."""
+    import torch
+    assert orc.orc_init(2) == 0
+    rng = np.random.default_rng(77 + n)
+    s = rng.integers(0, 2, n + 63, dtype=np.uint8)
+    if n > 100:
+        util.plant_syncwords(s, rng, max(1, n // 5000), 2)
+        util.plant_syncwords(s, rng, max(1, n // 20000), 4, laps=[0x123456])
+    sw = orc.orc_gen_syncword(0x123456)
+    for p in (0, n - 1, 4095, 4096, 4064):          # first / last position and strip seams
+        if 0 <= p < n:
+            s[p:p + 64] = [(sw >> i) & 1 for i in range(64)]
+    d_words = torch.from_numpy(_pack_words(s).view(np.int32)).cuda()
+    cap = n + 16
+    d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    for lap, k in [(B.LAP_ANY, 2), (B.LAP_ANY, 1), (B.LAP_ANY, 4), (0x123456, 2), (0x123456, 5), (0x123456, 20)]:
+        want = util.find_all(orc, "orc", s, n, lap, k)
+        cnt, rc = gpu_ctx2.find_ac_packed_dev(d_words.data_ptr(), n, d_hits.data_ptr(), cap, lap=lap, k=k)
+        assert rc == 0 and cnt == len(want), (n, hex(lap), k, cnt, len(want))
+        got = d_hits[:cnt].cpu().numpy().tobytes()
+        assert got == want.tobytes(), (n, hex(lap), k)
+
+
+def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc, monkeypatch):
+    """>= 4 Mi symbols: find_ac_host packs on the host before the copy; the byte-format copy
+    (BTBB_B200_HOST=bytes) and the oracle must give the same records, pageable memory included."""
+    assert orc.orc_init(2) == 0
+    rng = np.random.default_rng(99)
+    n = 6_000_011
+    s = rng.integers(0, 2, n + 63, dtype=np.uint8)
+    util.plant_syncwords(s, rng, 900, 2)
+    util.plant_syncwords(s, rng, 200, 3, laps=[0x9E8B33])
+    for lap, k in [(B.LAP_ANY, 2), (0x9E8B33, 3), (B.LAP_ANY, 3)]:
+        want = util.find_all(orc, "orc", s, n, lap, k)
+        got = gpu_ctx2.find_ac_host(s, n, lap, k)
+        assert got.tobytes() == want.tobytes(), (hex(lap), k, len(got), len(want))
+        monkeypatch.setenv("BTBB_B200_HOST", "bytes")
+        got2 = gpu_ctx2.find_ac_host(s, n, lap, k)
+        monkeypatch.delenv("BTBB_B200_HOST")
+        assert got2.tobytes() == want.tobytes(), ("bytes", hex(lap), k)

@@ -13,9 +13,14 @@ hn = hp.numpy().copy()
 ctx = B.Context(0, 2)
 cap = n // 10000 + (1 << 20)
 hits = np.zeros(cap, dtype=B.HIT_DTYPE); got = C.c_int64(0)
-for name, ptr in (("pinned", hp.data_ptr()), ("pageable", hn.ctypes.data)):
-    for it in range(3):
+import os as _os
+print("host threads", _os.cpu_count())
+for nt in _os.environ.get("PROBE_THREADS", "0").split(","):
+  if nt != "0":
+    _os.environ["BTBB_B200_PACK_THREADS"] = nt
+  for name, ptr in (("pinned", hp.data_ptr()), ("pageable", hn.ctypes.data)):
+    for it in range(4):
         t = time.perf_counter()
         B.check(lib.btbb_b200_find_ac_host(ctx.h, ptr, n, B.LAP_ANY, 2, hits.ctypes.data, cap, C.byref(got)))
         dt = time.perf_counter() - t
-        print(name, it, f"{dt*1e3:.1f} ms  {n/dt/1e9:.1f} GB/s  hits {got.value}")
+        print("threads", nt, name, it, f"{dt*1e3:.1f} ms  {n/dt/1e9:.1f} GB/s  hits {got.value}")
