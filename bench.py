@@ -82,6 +82,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def cpu_quota():
+    """CPUs the container may use at once (cgroup v2 cpu.max), or None when unlimited/unknown."""
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else round(int(q) / int(p), 2)
+    except Exception:
+        return None
+
+
 def cpu_scan_rate(sample_syms, min_seconds, threads, k):
     """Time the reference C path (or the oracle port) over a host-resident sample."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -117,7 +126,7 @@ def cpu_scan_rate(sample_syms, min_seconds, threads, k):
         total_t += fn(buf.ctypes.data, sample_syms, B.LAP_ANY, k, threads, C.byref(hits))
         total_s += sample_syms
         reps += 1
-    return {"value": total_s / total_t / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+    return {"value": total_s / total_t / 1e9, "unit": UNIT, "cores": threads, "cpu_quota": cpu_quota(), "kind": kind,
             "sample": f"{reps} x {sample_syms} symbols of the same synthetic stream (stride {STRIDE}, BER 0), "
                       f"promiscuous k={k}, contiguous chunks over {threads} pthreads, gcc -O2",
             "hits_per_pass": int(hits.value), "seconds": round(total_t, 3)}, total_t, reps

@@ -95,7 +95,8 @@ const char *btbb_b200_last_error(void);
  *   otherwise                -> find_known_lap semantics (:423-441)
  * d_stream must hold search_length + 63 readable symbols (the header asks for +72, btbb.h:82).
  * d_hits has room for max_hits records; *n_hits receives the total found (may exceed max_hits,
- * in which case BTBB_B200_EOVERFLOW is returned and the first max_hits records are valid).
+ * in which case BTBB_B200_EOVERFLOW is returned and d_hits holds max_hits genuine records in
+ * ascending order -- not necessarily the max_hits lowest offsets).
  * All work is enqueued on cuda_stream (a cudaStream_t passed as void*; NULL = default stream);
  * the call synchronises that stream before returning.
  */

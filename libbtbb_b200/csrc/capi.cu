@@ -6,9 +6,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <emmintrin.h>
 #include <pthread.h>
 #include <sched.h>
+#include <time.h>
 #include <atomic>
 #include <thread>
 #include <vector>
@@ -108,18 +108,15 @@ static int ensure_stage(btbb_b200_ctx *ctx, int64_t bytes)
 }
 
 /*
- * Host-buffer scan.  The stream is cut into chunks; chunk c is copied and scanned on
- * stream c&1, so the copy of one chunk overlaps the scan of the previous one.  Each chunk
- * carries a 63-symbol tail so windows that straddle a seam are seen exactly once.
+ * Host-buffer scan in the byte format.  The range is cut into chunks; chunk c is copied and
+ * scanned on stream c&1, so the copy of one chunk overlaps the scan of the previous one.
+ * Each chunk carries a 63-symbol tail so windows that straddle a seam are seen exactly once.
  * first_key != NULL selects first-hit mode (see push_hit in find_ac.cu).
  */
-static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_length, uint32_t lap,
-		     int max_ac_errors, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits,
-		     unsigned long long *first_key)
+static int scan_host_prepare(btbb_b200_ctx *ctx, int64_t span, int64_t max_hits, bool first_key, int64_t *chunk_out)
 {
-	BT_CUDA_TRY(cudaSetDevice(ctx->device));
 	const int64_t CHUNK = (int64_t)64 << 20;
-	int64_t chunk = search_length < CHUNK ? search_length : CHUNK;
+	int64_t chunk = span < CHUNK ? span : CHUNK;
 	int rc = ensure_stage(ctx, chunk + 64);
 	if (rc) return rc;
 	if (!first_key) {
@@ -134,15 +131,30 @@ static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_leng
 		}
 	}
 	BT_CUDA_TRY(cudaMemset(ctx->d_count, first_key ? 0xff : 0, sizeof(unsigned long long)));
+	*chunk_out = chunk;
+	return BTBB_B200_OK;
+}
+
+/* copies + scans of positions [0, span) of `stream`; nothing is waited for */
+static int scan_host_enqueue(btbb_b200_ctx *ctx, const char *stream, int64_t span, int64_t chunk, uint32_t lap,
+			     int max_ac_errors, int64_t max_hits, bool first_key)
+{
 	int c = 0;
-	for (int64_t pos = 0; pos < search_length; pos += chunk, c ^= 1) {
-		int64_t len = search_length - pos < chunk ? search_length - pos : chunk;
+	for (int64_t pos = 0; pos < span; pos += chunk, c ^= 1) {
+		int64_t len = span - pos < chunk ? span - pos : chunk;
 		cudaStream_t st = ctx->copy_stream[c];
 		BT_CUDA_TRY(cudaMemcpyAsync(ctx->d_stage[c], stream + pos, (size_t)(len + 63), cudaMemcpyHostToDevice, st));
-		rc = bt_scan_launch(ctx, ctx->d_stage[c], len, lap, max_ac_errors, ctx->d_tmp,
-				    first_key ? -1 : max_hits, ctx->d_count, pos, st);
+		int rc = bt_scan_launch(ctx, ctx->d_stage[c], len, lap, max_ac_errors, ctx->d_tmp,
+					first_key ? -1 : max_hits, ctx->d_count, pos, st);
 		if (rc) return rc;
 	}
+	return BTBB_B200_OK;
+}
+
+/* wait, order, bring the records back */
+static int scan_host_finish(btbb_b200_ctx *ctx, int64_t span, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits,
+			    unsigned long long *first_key)
+{
 	BT_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream[0]));
 	BT_CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream[1]));
 	unsigned long long total = 0;
@@ -153,7 +165,7 @@ static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_leng
 	*n_hits = (int64_t)total;
 	int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 	btbb_b200_hit *res = NULL;
-	rc = bt_sort_hits(ctx, ctx->d_tmp, ctx->d_tmp2, have, bt_sort_passes(search_length), ctx->copy_stream[0], &res);
+	int rc = bt_sort_hits(ctx, ctx->d_tmp, ctx->d_tmp2, have, bt_sort_passes(span), ctx->copy_stream[0], &res);
 	if (rc) return rc;
 	if (have > 0)
 		BT_CUDA_TRY(cudaMemcpyAsync(hits, res, (size_t)have * sizeof(btbb_b200_hit), cudaMemcpyDeviceToHost, ctx->copy_stream[0]));
@@ -163,33 +175,27 @@ static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_leng
 	return BTBB_B200_OK;
 }
 
+static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_length, uint32_t lap,
+		     int max_ac_errors, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits,
+		     unsigned long long *first_key)
+{
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	int64_t chunk = 0;
+	int rc = scan_host_prepare(ctx, search_length, max_hits, first_key != NULL, &chunk);
+	if (rc) return rc;
+	rc = scan_host_enqueue(ctx, stream, search_length, chunk, lap, max_ac_errors, max_hits, first_key != NULL);
+	if (rc) return rc;
+	return scan_host_finish(ctx, search_length, hits, max_hits, n_hits, first_key);
+}
+
 /* ---------------- host pack stage ----------------
  * The reference hands symbols over one per char (btbb.h:82-94); over PCIe that is 8 bits of
  * traffic per bit of information and the copy, not the scan, bounds a host-buffer call.  Large
- * calls therefore pack 32 symbols per word on the host (all cores, SSE2 movemask), copy the
+ * calls therefore pack 32 symbols per word on the host (host_pack.cpp, a few cores), copy the
  * packed words chunk by chunk while the next chunk is being packed, and run the packed
  * variants of the bulk kernels.  This is a change of transfer format only: every decision is
  * still made on the device. */
 namespace {
-
-inline uint32_t pack32_host(const char *p)
-{
-	const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p));
-	const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(p + 16));
-	return (uint32_t)_mm_movemask_epi8(_mm_slli_epi16(a, 7)) | ((uint32_t)_mm_movemask_epi8(_mm_slli_epi16(b, 7)) << 16);
-}
-
-/* symbols [first, first + 32 * nwords) -> out[0 .. nwords), never reading at or past `limit` */
-void pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out)
-{
-	int64_t w = 0;
-	for (; w < nwords && first + 32 * (w + 1) <= limit; w++) out[w] = pack32_host(stream + first + 32 * w);
-	for (; w < nwords; w++) {
-		uint32_t v = 0;
-		for (int j = 0; j < 32 && first + 32 * w + j < limit; j++) v |= (uint32_t)(stream[first + 32 * w + j] & 1) << j;
-		out[w] = v;
-	}
-}
 
 struct pack_job {
 	const char *stream;
@@ -220,7 +226,7 @@ void *pack_worker(void *p)
 			const int64_t a = j->next.fetch_add(BLOCK, std::memory_order_relaxed);
 			if (a >= nw) break;
 			const int64_t b = a + BLOCK < nw ? a + BLOCK : nw;
-			pack_range(j->stream, 32 * (w0 + a), b - a, j->limit, j->stage[c & 1] + a);
+			bt_pack_range(j->stream, 32 * (w0 + a), b - a, j->limit, j->stage[c & 1] + a);
 		}
 		pthread_barrier_wait(&j->done);
 	}
@@ -228,6 +234,35 @@ void *pack_worker(void *p)
 }
 
 }  // namespace
+
+/* CPUs this process may actually use: hardware threads, capped by a cgroup-v2 CPU quota */
+static int usable_cpus()
+{
+	int n = (int)std::thread::hardware_concurrency();
+	if (n < 1) n = 1;
+	if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+		long long quota = 0, period = 0;
+		if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0) {
+			const int q = (int)((quota + period - 1) / period);
+			if (q >= 1 && q < n) n = q;
+		}
+		fclose(f);
+	}
+	return n;
+}
+
+/* pack workers: every usable CPU up to 32 (BTBB_B200_PACK_THREADS overrides).  Measured on
+ * the B200 host (2 x 32 cores, 16-CPU quota): ~5 GB/s of symbols per thread, and threads
+ * beyond the quota only add throttling stalls at the per-chunk barriers. */
+static int pack_threads()
+{
+	int nt = usable_cpus();
+	if (nt > 32) nt = 32;
+	if (const char *e = getenv("BTBB_B200_PACK_THREADS")) nt = atoi(e);
+	if (nt < 1) nt = 1;
+	if (nt > 128) nt = 128;
+	return nt;
+}
 
 /* stream[0 .. nsym) -> ctx->d_packed (ceil(nsym / 32) words), copies issued on copy_stream[0] */
 static int pack_and_upload(btbb_b200_ctx *ctx, const char *stream, int64_t nsym)
@@ -259,13 +294,7 @@ static int pack_and_upload(btbb_b200_ctx *ctx, const char *stream, int64_t nsym)
 	job.chunk_words = chunk_words; job.total_words = total_words;
 	job.nchunks = (total_words + chunk_words - 1) / chunk_words;
 	job.stage[0] = ctx->h_pack[0]; job.stage[1] = ctx->h_pack[1];
-	/* measured on a 2 x 32-core host (profiles/README.md): 16 threads already pack faster than
-	 * PCIe copies the bytes would take; more threads gain little and get unstable under a CPU quota */
-	int nt = (int)std::thread::hardware_concurrency();
-	if (nt > 16) nt = 16;
-	if (const char *e = getenv("BTBB_B200_PACK_THREADS")) nt = atoi(e);
-	if (nt < 1) nt = 1;
-	if (nt > 128) nt = 128;
+	int nt = pack_threads();
 	if ((int64_t)nt > (chunk_words + 65535) / 65536) nt = (int)((chunk_words + 65535) / 65536);
 	job.ready.store(0);
 	std::vector<pthread_t> th((size_t)nt);
@@ -305,14 +334,59 @@ static int pack_and_upload(btbb_b200_ctx *ctx, const char *stream, int64_t nsym)
 	return BTBB_B200_OK;
 }
 
-/* large host-buffer call: pack, upload, scan the packed stream, bring the ordered hits back */
+static double now_ms()
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+/*
+ * Large host-buffer call: the host cores pack the stream while it is copied, the packed bulk
+ * kernels scan it.  Optionally (BTBB_B200_HOST_SPLIT=<fraction>) the head [0, split) travels
+ * in the byte format instead -- DMA straight from a pinned buffer, no CPU work, scanned chunk
+ * by chunk as it arrives -- while the cores pack the rest.  On the B200 host this was
+ * measured as no gain (profiles/README.md: DMA and pack threads compete for the same host
+ * memory bandwidth, ~80 GB/s in total), so the default split is 0; a host with spare memory
+ * bandwidth would set it near 0.35.  Both parts partition the positions exactly, so the
+ * concatenation of their hit lists is the ascending list.
+ */
 static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t search_length, uint32_t lap,
 			    int max_ac_errors, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits)
 {
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
-	int rc = pack_and_upload(ctx, stream, search_length + 63);
+	const bool trace = getenv("BTBB_B200_TRACE") != NULL;
+	const double t0 = trace ? now_ms() : 0;
+	int64_t split = 0;
+	{
+		double frac = 0;
+		if (const char *e = getenv("BTBB_B200_HOST_SPLIT")) frac = atof(e);
+		if (frac < 0) frac = 0;
+		if (frac > 0.95) frac = 0.95;
+		split = (int64_t)(frac * (double)search_length) & ~(int64_t)4095;
+	}
+	int rc;
+	int64_t chunk = 0;
+	if (split > 0) {
+		rc = scan_host_prepare(ctx, split, max_hits, false, &chunk);
+		if (rc) return rc;
+		rc = scan_host_enqueue(ctx, stream, split, chunk, lap, max_ac_errors, max_hits, false);
+		if (rc) return rc;
+	}
+	rc = pack_and_upload(ctx, stream + split, search_length - split + 63);
 	if (rc) return rc;
-	const int64_t cap = max_hits > 0 ? max_hits : 1;
+	const double t1 = trace ? now_ms() : 0;
+	int64_t n_a = 0;
+	bool overflow = false;
+	if (split > 0) {
+		rc = scan_host_finish(ctx, split, hits, max_hits, &n_a, NULL);
+		if (rc == BTBB_B200_EOVERFLOW) overflow = true;
+		else if (rc) return rc;
+	}
+	const double t2 = trace ? now_ms() : 0;
+	const int64_t have_a = n_a < max_hits ? n_a : max_hits;
+	const int64_t room = max_hits - have_a;
+	const int64_t cap = room > 0 ? room : 1;
 	if (cap > ctx->tmp2_cap) {
 		if (ctx->d_tmp2) cudaFree(ctx->d_tmp2);
 		ctx->d_tmp2 = NULL; ctx->tmp2_cap = 0;
@@ -320,14 +394,25 @@ static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t sear
 		ctx->tmp2_cap = cap;
 	}
 	cudaStream_t st = ctx->copy_stream[0];
-	rc = bt_find_ac_dev_impl(ctx, reinterpret_cast<const uint8_t *>(ctx->d_packed), 1, search_length, lap,
-				 max_ac_errors, ctx->d_tmp2, max_hits, n_hits, st);
-	if (rc != BTBB_B200_OK && rc != BTBB_B200_EOVERFLOW) return rc;
-	const int64_t have = *n_hits < max_hits ? *n_hits : max_hits;
-	if (have > 0)
-		BT_CUDA_TRY(cudaMemcpyAsync(hits, ctx->d_tmp2, (size_t)have * sizeof(btbb_b200_hit), cudaMemcpyDeviceToHost, st));
+	int64_t n_b = 0;
+	rc = bt_find_ac_dev_impl(ctx, reinterpret_cast<const uint8_t *>(ctx->d_packed), 1, search_length - split, lap,
+				 max_ac_errors, ctx->d_tmp2, room, &n_b, st);
+	if (rc == BTBB_B200_EOVERFLOW) overflow = true;
+	else if (rc) return rc;
+	const int64_t have_b = n_b < room ? n_b : room;
+	if (have_b > 0)
+		BT_CUDA_TRY(cudaMemcpyAsync(hits + have_a, ctx->d_tmp2, (size_t)have_b * sizeof(btbb_b200_hit), cudaMemcpyDeviceToHost, st));
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
-	return rc;
+	if (split > 0)
+		for (int64_t i = 0; i < have_b; i++) hits[have_a + i].offset += split;
+	*n_hits = n_a + n_b;
+	if (trace)
+		fprintf(stderr, "[btbb_b200] find_ac_host: %lld symbols as bytes + %lld packed (%d threads): issue+pack %.2f ms, "
+			"byte part drained %.2f ms, packed scan+readback %.2f ms\n", (long long)split,
+			(long long)(search_length - split), pack_threads(), t1 - t0, t2 - t1, now_ms() - t2);
+	if (overflow)
+		return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac_host: hit buffer too small");
+	return BTBB_B200_OK;
 }
 
 extern "C" int btbb_b200_find_ac_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_length,

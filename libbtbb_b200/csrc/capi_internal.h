@@ -93,6 +93,9 @@ int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t
 		 int passes, cudaStream_t st, btbb_b200_hit **result);
 int bt_sort_passes(int64_t span);
 
+/* host_pack.cpp */
+extern "C" void bt_pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out);
+
 /* capi.cu */
 int bt_find_first_host(btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,
 		       int max_ac_errors, btbb_b200_hit *hit, int *found);

@@ -46,3 +46,26 @@ def test_fails_loudly_without_cuda(product_lib):
     rc = product_lib.btbb_b200_create(0, 2, C.byref(h))
     assert rc == -2 and not h.value            # no CPU fallback: creation fails
     assert b"no CUDA device" in product_lib.btbb_b200_last_error()
+
+
+def test_host_pack_bit_order_and_limit(product_lib):
+    """host half of the packed transfer format: symbol i -> bit i & 31 of word i >> 5, nothing
+    read at or past the limit (no GPU involved)."""
+    import ctypes as C
+    import numpy as np
+    f = product_lib.bt_pack_range
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    f.restype = None
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 32, 33, 127, 128, 129, 1000, 4096 + 17):
+        s = rng.integers(0, 2, n, dtype=np.uint8)
+        guard = np.concatenate([s, np.full(64, 0xFF, dtype=np.uint8)])     # poison past the limit
+        for first in (0, 32, 96):
+            if first >= n:
+                continue
+            nwords = (n - first + 31) // 32
+            out = np.zeros(nwords, dtype=np.uint32)
+            f(guard.ctypes.data, first, nwords, n, out.ctypes.data)
+            pad = (-(n - first)) % 32
+            want = np.packbits(np.concatenate([s[first:], np.zeros(pad, dtype=np.uint8)]), bitorder="little").view("<u4")
+            assert (out == want).all(), (n, first)

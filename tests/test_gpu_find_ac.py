@@ -203,3 +203,28 @@ def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc, monkeypatch):
         got2 = gpu_ctx2.find_ac_host(s, n, lap, k)
         monkeypatch.delenv("BTBB_B200_HOST")
         assert got2.tobytes() == want.tobytes(), ("bytes", hex(lap), k)
+        # head as bytes over DMA, rest packed (what a pinned buffer gets), forced split points
+        for frac in ("0.37", "0.0007", "0.95"):
+            monkeypatch.setenv("BTBB_B200_HOST_SPLIT", frac)
+            got3 = gpu_ctx2.find_ac_host(s, n, lap, k)
+            monkeypatch.delenv("BTBB_B200_HOST_SPLIT")
+            assert got3.tobytes() == want.tobytes(), ("split", frac, hex(lap), k)
+    import torch
+    pinned = torch.from_numpy(s).pin_memory()
+    want = util.find_all(orc, "orc", s, n, B.LAP_ANY, 2)
+    got4 = gpu_ctx2.find_ac_host(pinned.numpy(), n, B.LAP_ANY, 2)
+    assert got4.tobytes() == want.tobytes()
+    # a hit buffer that is too small: EOVERFLOW, the full count, and max_hits genuine records in
+    # ascending order (which ones is not specified) on every route
+    import ctypes as C
+    few = np.zeros(50, dtype=B.HIT_DTYPE)
+    cnt = C.c_int64(0)
+    for env in (None, "0.5"):
+        if env:
+            monkeypatch.setenv("BTBB_B200_HOST_SPLIT", env)
+        rc = B.lib().btbb_b200_find_ac_host(gpu_ctx2.h, s.ctypes.data, n, B.LAP_ANY, 2, few.ctypes.data, 50, C.byref(cnt))
+        if env:
+            monkeypatch.delenv("BTBB_B200_HOST_SPLIT")
+        assert rc == -4 and cnt.value == len(want), (env, rc, cnt.value)
+        wanted = {r.tobytes() for r in want}
+        assert all(r.tobytes() in wanted for r in few) and (np.diff(few["offset"]) > 0).all(), env
