@@ -389,6 +389,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 #include "scan_v3.cuh"
 #include "scan_v4.cuh"
 #include "scan_v6.cuh"
+#include "scan_v7.cuh"
 #include "scan_known.cuh"
 
 }  // namespace
@@ -603,6 +604,25 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		else if (env && !strcmp(env, "v6w24s4")) kern = v6::scan_promisc_v6<4, 24>;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v6::SMEM_BYTES));
 		kern<<<(unsigned)grid, bulk_warps * 32, v6::SMEM_BYTES, st>>>(a);
+	} else if (env && !strncmp(env, "v7", 2)) {
+		/* developer switch: v7 = multiply windows, v7f = funnel-shift windows; a trailing 'a'
+		 * selects layout<1> (table A by byte permute, 32 KiB map); s4 / s6 = inline slots */
+		v7::args a;
+		const bool ta = strchr(env + 2, 'a') != NULL;
+		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
+		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const v3::xparams *)slot;
+		a.m1 = 0xffffffffu; a.c64 = 64u;
+		void (*kern)(const v7::args) = v7::scan_promisc_v7<1, 5, 0>;
+		if (!strcmp(env, "v7f")) kern = v7::scan_promisc_v7<0, 5, 0>;
+		else if (!strcmp(env, "v7fa")) kern = v7::scan_promisc_v7<0, 5, 1>;
+		else if (!strcmp(env, "v7a")) kern = v7::scan_promisc_v7<1, 5, 1>;
+		else if (!strcmp(env, "v7fs4")) kern = v7::scan_promisc_v7<0, 4, 0>;
+		else if (!strcmp(env, "v7fs6")) kern = v7::scan_promisc_v7<0, 6, 0>;
+		else if (!strcmp(env, "v7fas4")) kern = v7::scan_promisc_v7<0, 4, 1>;
+		else if (!strcmp(env, "v7fas6")) kern = v7::scan_promisc_v7<0, 6, 1>;
+		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
+		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);
 	} else if (env && !strcmp(env, "v3")) {
 		v3::args a;
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
