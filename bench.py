@@ -265,7 +265,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     alg_bytes = n + 63 + 16 * local_hits          # 1 B read per position + 16 B per hit
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "scan_promisc_v4 (bulk) + tile kernel on the ragged tail", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "scan_promisc_v7<0,5,1> (bulk, scan_v7.cuh) + tile kernel on the ragged tail", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms}
     tf = os.path.join(ROOT, "profiles", "traffic.json")

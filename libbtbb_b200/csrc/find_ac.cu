@@ -510,10 +510,14 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	}
 	if (packed) env = NULL;      /* the developer switches below are for the byte format */
-	/* promiscuous default: scan_v4.cuh (LUTMODE 2, five in-place slots).  BTBB_B200_SCAN=v6..
-	 * selects the experimental scan_v6.cuh, whose windows start one symbol before the aligned
-	 * data it loads (so it wants at least one symbol in front); v3 / v4a.. the older variants */
+	/* promiscuous default: scan_v7.cuh for the byte format, scan_v4.cuh (LUTMODE 2, five in-place
+	 * slots) for packed input.  BTBB_B200_SCAN=v6.. selects the experimental scan_v6.cuh, whose
+	 * windows start one symbol before the aligned data it loads (so it wants at least one symbol
+	 * in front); v3 / v4a.. the older generations, v7 / v7f / .. the v7 variants */
 	const bool use_v6 = !known && !packed && env && !strncmp(env, "v6", 2);
+	/* byte-format promiscuous scans run scan_v7.cuh unless an older generation is asked for */
+	const bool use_v7 = !known && !packed && !use_v6 && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3")));
+	const char *env7 = env && !strncmp(env, "v7", 2) ? env : NULL;
 	int64_t al = packed ? 0 : (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
 	if (use_v6 && al == 0) al = 32;
 	const int64_t head = use_v6 ? al - 1 : al;                                             /* first window of the bulk kernel */
@@ -592,6 +596,25 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 			else kern = inv2 ? vk::scan_known_v4<false, true, true, true> : vk::scan_known_v4<false, true, false, true>;
 		}
 		kern<<<(unsigned)grid, vk::WARPS * 32, vk::SMEM_BYTES, st>>>(a);
+	} else if (use_v7) {
+		/* developer switch: v7 = multiply windows, v7f = funnel-shift windows; a trailing 'a'
+		 * selects layout<1> (table A by byte permute, 32 KiB map); s4 / s6 = inline slots */
+		v7::args a;
+		const bool ta = !env7 || strchr(env7 + 2, 'a') != NULL;
+		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
+		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const v3::xparams *)slot;
+		a.m1 = 0xffffffffu; a.c64 = 64u;
+		void (*kern)(const v7::args) = v7::scan_promisc_v7<0, 5, 1>;       /* shipped */
+		if (env7 && !strcmp(env7, "v7")) kern = v7::scan_promisc_v7<1, 5, 0>;
+		else if (env7 && !strcmp(env7, "v7f")) kern = v7::scan_promisc_v7<0, 5, 0>;
+		else if (env7 && !strcmp(env7, "v7a")) kern = v7::scan_promisc_v7<1, 5, 1>;
+		else if (env7 && !strcmp(env7, "v7fs4")) kern = v7::scan_promisc_v7<0, 4, 0>;
+		else if (env7 && !strcmp(env7, "v7fs6")) kern = v7::scan_promisc_v7<0, 6, 0>;
+		else if (env7 && !strcmp(env7, "v7fas4")) kern = v7::scan_promisc_v7<0, 4, 1>;
+		else if (env7 && !strcmp(env7, "v7fas6")) kern = v7::scan_promisc_v7<0, 6, 1>;
+		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
+		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);
 	} else if (use_v6) {
 		v6::args a;
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
@@ -604,25 +627,6 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		else if (env && !strcmp(env, "v6w24s4")) kern = v6::scan_promisc_v6<4, 24>;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v6::SMEM_BYTES));
 		kern<<<(unsigned)grid, bulk_warps * 32, v6::SMEM_BYTES, st>>>(a);
-	} else if (env && !strncmp(env, "v7", 2)) {
-		/* developer switch: v7 = multiply windows, v7f = funnel-shift windows; a trailing 'a'
-		 * selects layout<1> (table A by byte permute, 32 KiB map); s4 / s6 = inline slots */
-		v7::args a;
-		const bool ta = strchr(env + 2, 'a') != NULL;
-		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
-		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const v3::xparams *)slot;
-		a.m1 = 0xffffffffu; a.c64 = 64u;
-		void (*kern)(const v7::args) = v7::scan_promisc_v7<1, 5, 0>;
-		if (!strcmp(env, "v7f")) kern = v7::scan_promisc_v7<0, 5, 0>;
-		else if (!strcmp(env, "v7fa")) kern = v7::scan_promisc_v7<0, 5, 1>;
-		else if (!strcmp(env, "v7a")) kern = v7::scan_promisc_v7<1, 5, 1>;
-		else if (!strcmp(env, "v7fs4")) kern = v7::scan_promisc_v7<0, 4, 0>;
-		else if (!strcmp(env, "v7fs6")) kern = v7::scan_promisc_v7<0, 6, 0>;
-		else if (!strcmp(env, "v7fas4")) kern = v7::scan_promisc_v7<0, 4, 1>;
-		else if (!strcmp(env, "v7fas6")) kern = v7::scan_promisc_v7<0, 6, 1>;
-		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
-		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);
 	} else if (env && !strcmp(env, "v3")) {
 		v3::args a;
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;

@@ -62,6 +62,44 @@ def test_dense_hits_known_lap(gpu_ctx2, orc):
     assert len(gpu_ctx2.find_ac_host(s, n, 0x9E8B33, 64, max_hits=n)) == n
 
 
+def _barker_dense_streams(rng, n):
+    """Streams on which far more than 1/8 of all positions pass the Barker-tail filter, up to
+    nearly all of them: they overflow the bulk kernel's per-warp candidate queue and force its
+    in-place fallback."""
+    out = {}
+    a = np.array([(0x27 >> i) & 1 for i in range(7)], dtype=np.uint8)         # tail A, period 7
+    out["tailA_period7"] = np.resize(a, n + 63)
+    out["ones"] = np.ones(n + 63, dtype=np.uint8)
+    out["zeros"] = np.zeros(n + 63, dtype=np.uint8)
+    s = np.resize(a, n + 63).copy()                                           # tail A with 3 % flips
+    s ^= (rng.random(n + 63) < 0.03).astype(np.uint8)
+    out["tailA_noisy"] = s
+    words = []                                                                # back-to-back sync words
+    laps = rng.integers(0, 1 << 24, (n + 63) // 64 + 1)
+    for lap in laps:
+        w = int(B.lib().btbb_gen_syncword(int(lap))) & 0xFFFFFFFFFFFFFFFF
+        words.append([(w >> i) & 1 for i in range(64)])
+    s = np.array(words, dtype=np.uint8).reshape(-1)[: n + 63].copy()
+    s ^= (rng.random(n + 63) < 0.01).astype(np.uint8)
+    out["syncwords_back_to_back"] = s
+    s = rng.integers(0, 2, n + 63, dtype=np.uint8)                            # half dense, half noise
+    s[: n // 2] = np.resize(a, n // 2)
+    out["half_dense"] = s
+    return out
+
+
+def test_barker_dense_streams(gpu_ctx2, orc, product_lib):
+    assert orc.orc_init(2) == 0
+    product_lib.btbb_gen_syncword.restype = C.c_uint64
+    rng = np.random.default_rng(77)
+    n = 150_000
+    for name, s in _barker_dense_streams(rng, n).items():
+        for k in (0, 2):
+            want = util.find_all(orc, "orc", s, n, B.LAP_ANY, k)
+            got = gpu_ctx2.find_ac_host(s, n, B.LAP_ANY, k, max_hits=n)
+            assert got.tobytes() == want.tobytes(), (name, k, len(got), len(want))
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 63, 64, 65, 8191, 8192, 8193, 16384 + 5])
 def test_edge_lengths_and_seams(gpu_ctx2, orc, n):
     """Tiny and tile-boundary lengths; hits planted at the first/last position and on seams."""
