@@ -122,7 +122,7 @@ def cpu_scan_rate(sample_syms, min_seconds, threads, k):
     hits = C.c_int64(0)
     fn(buf.ctypes.data, min(sample_syms, 1 << 24), B.LAP_ANY, k, threads, C.byref(hits))   # warm-up
     total_t, total_s, reps = 0.0, 0, 0
-    while total_t < min_seconds and reps < 64:
+    while (reps == 0 or total_t < min_seconds) and reps < 64:
         total_t += fn(buf.ctypes.data, sample_syms, B.LAP_ANY, k, threads, C.byref(hits))
         total_s += sample_syms
         reps += 1
