@@ -155,6 +155,50 @@ int btbb_b200_header_present_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, in
 				 const btbb_b200_pkt_in *d_pkts, int64_t n,
 				 uint8_t *d_present, void *cuda_stream);
 
+/*
+ * UAP / CLK1-6 discovery from packet headers: btbb_uap_from_header (bluetooth_piconet.c:648-750)
+ * as btbb_process_packet drives it in survey mode (:851-858), for many piconets at once
+ * (SURVEY.md 8(f) row 1).  btbb_b200_sieve is the part of struct btbb_piconet
+ * (bluetooth_piconet.h:30-105) those two functions read and write; flag bit numbers are the
+ * reference's (btbb.h:27-42).  A zeroed record is a freshly calloc'ed piconet.
+ */
+typedef struct btbb_b200_sieve {
+	uint32_t flags;                  /* BTBB_UAP_VALID 2, BTBB_CLK6_VALID 4, BTBB_CLK27_VALID 5, BTBB_HOP_REVERSAL_INIT 9,
+	                                    BTBB_GOT_FIRST_PACKET 10, BTBB_IS_AFH 11, BTBB_LOOKS_LIKE_AFH 12 */
+	uint32_t first_pkt_time;         /* pn->first_pkt_time */
+	int32_t  clk_offset;             /* pn->clk_offset */
+	int32_t  packets_observed;       /* pn->packets_observed */
+	int32_t  total_packets_observed; /* pn->total_packets_observed */
+	uint8_t  uap;                    /* pn->UAP */
+	uint8_t  used_channels;          /* pn->used_channels */
+	uint8_t  afh_map[10];            /* pn->afh_map (btbb_piconet_set_channel_seen) */
+	int16_t  clock6_candidates[64];  /* pn->clock6_candidates: -1 eliminated, else the UAP that clock implies */
+} btbb_b200_sieve;
+
+#define BTBB_B200_SIEVE_NOT_CALLED (-2)  /* rv: header absent or UAP already known -> btbb_uap_from_header not called */
+
+/*
+ * For every group g (one piconet, i.e. one LAP), packets [group_start[g], group_start[g+1]) of
+ * d_pkts are its packets in arrival order.  Each is handled as btbb_process_packet does in survey
+ * mode: btbb_piconet_set_channel_seen(channel), then, if btbb_header_present(pkt) and the UAP is
+ * not known yet, btbb_uap_from_header(pkt, pn).  The channel is the low byte of
+ * btbb_b200_pkt_in.reserved, clkn is the packet's CLKN as btbb_packet_set_data stores it.
+ * d_states[g] is read, updated and written back, so a capture can be fed in several calls.
+ * d_rv[p] receives btbb_uap_from_header's return value (0 / 1) or BTBB_B200_SIEVE_NOT_CALLED;
+ * it may be NULL.  The 64 try_clock / crc_check evaluations per packet run on the GPU in one
+ * pass over all packets, the (sequential per piconet) candidate elimination one warp per piconet.
+ * The hop-pattern log (pattern_indices / pattern_channels) is not kept: hop reversal is out
+ * of scope; the 1000-packet limit that resets a piconet (:665-671) is honoured.
+ */
+int btbb_b200_uap_sieve_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+			    const btbb_b200_pkt_in *d_pkts, int64_t n_pkts,
+			    const int64_t *d_group_start, int64_t n_groups,
+			    btbb_b200_sieve *d_states, int8_t *d_rv, void *cuda_stream);
+int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
+			     const btbb_b200_pkt_in *pkts, int64_t n_pkts,
+			     const int64_t *group_start, int64_t n_groups,
+			     btbb_b200_sieve *states, int8_t *rv);
+
 /* ---- synthetic capture generator (SURVEY.md 8d "Synthetic input"; test/bench data only) ---- */
 typedef struct btbb_b200_synth_cfg {
 	uint64_t seed;          /* 0xB200B7BB by default */
@@ -165,7 +209,7 @@ typedef struct btbb_b200_synth_cfg {
 	uint32_t ber_q32;       /* bit-flip probability * 2^32 applied to every symbol */
 	uint32_t packet_mix;    /* bit i set => packet kind i may be planted (see BTBB_B200_KIND_*) */
 	uint32_t fixed_lap;     /* if n_laps == 1: the LAP to plant */
-	uint32_t reserved;
+	uint32_t reserved;      /* bit 0: piconet-coherent capture (one UAP per LAP, CLK1-6 = slot + a per-LAP offset) */
 } btbb_b200_synth_cfg;
 
 #define BTBB_B200_KIND_ID    0   /* 68-symbol ID packet: access code only */

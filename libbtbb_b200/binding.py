@@ -45,6 +45,12 @@ DECODED_DTYPE = np.dtype([("header_ok", "<i4"), ("rv", "<i4"), ("uap", "u1"), ("
                           ("payload", "u1", (344,))])
 PKTIN_DTYPE = np.dtype([("offset", "<i8"), ("length", "<i4"), ("clkn", "<u4"), ("uap", "u1"),
                         ("whitened", "u1"), ("type", "u1"), ("pad", "u1"), ("reserved", "<u4")])
+SIEVE_DTYPE = np.dtype([("flags", "<u4"), ("first_pkt_time", "<u4"), ("clk_offset", "<i4"), ("packets_observed", "<i4"),
+                        ("total_packets_observed", "<i4"), ("uap", "u1"), ("used_channels", "u1"), ("afh_map", "u1", (10,)),
+                        ("clock6_candidates", "<i2", (64,))])
+SIEVE_NOT_CALLED = -2
+F_UAP_VALID, F_CLK6_VALID, F_GOT_FIRST_PACKET = 1 << 2, 1 << 4, 1 << 10
+assert SIEVE_DTYPE.itemsize == 160
 assert HIT_DTYPE.itemsize == C.sizeof(Hit) == 16
 assert DECODED_DTYPE.itemsize == C.sizeof(Decoded) == 372
 assert PKTIN_DTYPE.itemsize == C.sizeof(PktIn) == 24
@@ -66,6 +72,8 @@ _PROTOS = {
     "btbb_b200_decode_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "btbb_b200_decode_host": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp]),
     "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_synth_host": (_int, [C.POINTER(SynthCfg), _vp]),
     "btbb_b200_synth_dev": (_int, [C.POINTER(SynthCfg), _vp, _vp]),
     "btbb_b200_synth_planted": (_int, [C.POINTER(SynthCfg), _i64, C.POINTER(Planted)]),
@@ -117,12 +125,12 @@ def check(rc, allow=()):
 
 
 def synth_cfg(n_symbols, stride=10000, n_laps=64, ber=0.0, mix=("DM1", "DM3", "DH1", "FHS"),
-              seed=DEFAULT_SEED, first_symbol=0, fixed_lap=0x9E8B33):
+              seed=DEFAULT_SEED, first_symbol=0, fixed_lap=0x9E8B33, piconets=False):
     m = 0
     for k in mix:
         m |= 1 << KIND[k]
     return SynthCfg(seed=seed, n_symbols=n_symbols, first_symbol=first_symbol, stride=stride, n_laps=n_laps,
-                    ber_q32=min(int(ber * 2 ** 32), 2 ** 32 - 1), packet_mix=m, fixed_lap=fixed_lap, reserved=0)
+                    ber_q32=min(int(ber * 2 ** 32), 2 ** 32 - 1), packet_mix=m, fixed_lap=fixed_lap, reserved=1 if piconets else 0)
 
 
 def synth_host(cfg):
@@ -177,6 +185,17 @@ class Context:
                                                 C.byref(n), stream)
         check(rc, allow=(-4,))
         return n.value, rc
+
+    def uap_sieve_host(self, stream, pkts, group_start, states):
+        """btbb_b200_uap_sieve_host: returns (updated states, rv per packet)."""
+        assert stream.dtype == np.uint8 and pkts.dtype == PKTIN_DTYPE and states.dtype == SIEVE_DTYPE
+        gs = np.ascontiguousarray(group_start, dtype=np.int64)
+        assert len(gs) == len(states) + 1 and gs[-1] <= len(pkts)
+        st = states.copy()
+        rv = np.zeros(len(pkts), dtype=np.int8)
+        check(lib().btbb_b200_uap_sieve_host(self.h, stream.ctypes.data, len(stream), pkts.ctypes.data, len(pkts),
+                                             gs.ctypes.data, len(st), st.ctypes.data, rv.ctypes.data))
+        return st, rv
 
     def decode_host(self, stream, pkts, mode=0):
         assert stream.dtype == np.uint8 and pkts.dtype == PKTIN_DTYPE

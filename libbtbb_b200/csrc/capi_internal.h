@@ -68,6 +68,9 @@ struct btbb_b200_ctx {
 	int64_t h_pack_cap;          /* words each */
 	int64_t stage_cap;
 	cudaStream_t copy_stream[2];
+	uint16_t *d_sieve_tc;        /* UAP sieve: (packet, clock) table, 64 words per packet */
+	uint8_t *d_sieve_present;    /* UAP sieve: btbb_header_present per packet */
+	int64_t sieve_cap;           /* packets the two buffers hold */
 };
 
 int btbb_b200_set_error(int code, const char *msg);
@@ -95,6 +98,10 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t have,
 		 int passes, cudaStream_t st, btbb_b200_hit **result);
 int bt_sort_passes(int64_t span);
+
+/* decode.cu */
+int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+			  const btbb_b200_pkt_in *d_pkts, int64_t n, uint16_t *d_tc, cudaStream_t st);
 
 /* host_pack.cpp */
 extern "C" void bt_pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out);

@@ -335,7 +335,7 @@ __device__ __forceinline__ bool fec23_block(uint32_t cw15, const uint8_t *col, u
 
 __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const uint8_t *stream, int64_t stream_len,
 							     const btbb_b200_pkt_in *pkts, int64_t n, int mode,
-							     btbb_b200_decoded *out)
+							     btbb_b200_decoded *out, uint16_t *tc16)
 {
 	__shared__ warp_smem s_w[WARPS];
 	__shared__ uint32_t s_wseq[13];
@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const uint8_t *strea
 					s.type = (hp >> 3) & 15;
 				}
 				int rv = do_crc_check(d, s, clock);
-				emit_record(d, s, ok, rv, 0, &out[p * 64 + clock]);
+				if (tc16)      /* compact table for the UAP / CLK1-6 sieve (sieve.cu): UAP | class << 8 */
+					tc16[p * 64 + clock] = (uint16_t)(s.uap | ((rv == 0 ? 0 : rv == 1 ? 1 : rv == 2 ? 2 : rv == 10 ? 3 : 4) << 8));
+				else
+					emit_record(d, s, ok, rv, 0, &out[p * 64 + clock]);
 			}
 		}
 		__syncwarp();
@@ -532,7 +535,24 @@ extern "C" int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream,
 	int64_t blocks = (n + WARPS - 1) / WARPS;
 	int64_t cap = (int64_t)ctx->sm_count * 16;
 	if (blocks > cap) blocks = cap;
-	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, (cudaStream_t)cuda_stream>>>(d_stream, stream_length, d_pkts, n, mode, d_out);
+	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, (cudaStream_t)cuda_stream>>>(d_stream, stream_length, d_pkts, n, mode, d_out, NULL);
+	BT_CUDA_TRY(cudaGetLastError());
+	return BTBB_B200_OK;
+}
+
+/* try_clock + crc_check for CLK1-6 = 0..63 of n packets (bluetooth_piconet.c:675-689), results
+ * as one 16-bit word per (packet, clock): the UAP try_clock returned in the low byte, the
+ * crc_check class above it (0, 1, 2 as returned; 3 = 10; 4 = 1000) */
+int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+			  const btbb_b200_pkt_in *d_pkts, int64_t n, uint16_t *d_tc, cudaStream_t st)
+{
+	int rc = upload_dec_tables(ctx->device);
+	if (rc) return rc;
+	if (n == 0) return BTBB_B200_OK;
+	int64_t blocks = (n + WARPS - 1) / WARPS;
+	int64_t cap = (int64_t)ctx->sm_count * 16;
+	if (blocks > cap) blocks = cap;
+	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, st>>>(d_stream, stream_length, d_pkts, n, BTBB_B200_MODE_TRY_CLOCKS, NULL, d_tc);
 	BT_CUDA_TRY(cudaGetLastError());
 	return BTBB_B200_OK;
 }

@@ -90,6 +90,13 @@ BT_HD void synth_params(const btbb_b200_synth_cfg *c, int64_t slot, btbb_b200_pl
 	p->uap = (uint8_t)(r1 & 0xff);
 	p->kind = (uint8_t)kind;
 	p->clk6 = (uint8_t)((r1 >> 8) & 0x3f);
+	if (c->reserved & 1u) {
+		/* piconet-coherent capture: one UAP per LAP and a piconet clock that advances by one per
+		 * slot (a receiver that stamps packet `slot` with CLKN = slot sees CLK1-6 = CLKN + offset) */
+		uint64_t rl = bt_splitmix64(c->seed ^ 0x5049434FULL ^ ((uint64_t)p->lap * 0x9E3779B97F4A7C15ULL));
+		p->uap = (uint8_t)(rl & 0xff);
+		p->clk6 = (uint8_t)(((rl >> 8) + (uint64_t)slot) & 0x3f);
+	}
 	p->lt_addr = (uint8_t)(1 + ((r1 >> 16) % 7));
 	p->n_symbols = n;
 	p->body_bytes = body;

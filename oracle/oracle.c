@@ -687,3 +687,105 @@ int orc_header_present(const char *s, int length)
 	}
 	return be < 5;
 }
+
+/* ---- UAP / CLK1-6 discovery ----
+ * btbb_process_packet in survey mode (bluetooth_piconet.c:851-858) around btbb_uap_from_header
+ * (:648-750), for packets grouped by piconet.  Sequential, one packet object reused across the
+ * 64 candidates exactly as the reference does. */
+#define OF_UAP_VALID (1u << 2)
+#define OF_CLK6_VALID (1u << 4)
+#define OF_CLK27_VALID (1u << 5)
+#define OF_HOP_INIT (1u << 9)
+#define OF_GOT_FIRST (1u << 10)
+#define OF_IS_AFH (1u << 11)
+#define OF_LOOKS_AFH (1u << 12)
+
+static void sieve_reset(btbb_b200_sieve *pn)                 /* reset(), :547-568 */
+{
+	pn->flags &= ~(OF_GOT_FIRST | OF_HOP_INIT | OF_UAP_VALID | OF_CLK6_VALID | OF_CLK27_VALID | OF_IS_AFH);
+	if (pn->flags & OF_LOOKS_AFH) pn->flags |= OF_IS_AFH;
+	pn->packets_observed = 0;
+}
+
+static void sieve_channel_seen(btbb_b200_sieve *pn, unsigned channel)   /* :142-150 */
+{
+	if (channel >= 80) return;
+	if (!(pn->afh_map[channel / 8] & (1u << (channel % 8)))) {
+		pn->afh_map[channel / 8] |= (uint8_t)(1u << (channel % 8));
+		pn->used_channels++;
+	}
+}
+
+static int sieve_uap_from_header(opkt *pkt, uint32_t clkn, unsigned channel, btbb_b200_sieve *pn)
+{
+	int count, remaining = 0, first_clock = 0;
+	if (!(pn->flags & OF_GOT_FIRST)) pn->first_pkt_time = clkn;
+	sieve_channel_seen(pn, channel);
+	if (pn->packets_observed >= 1000) {                     /* MAX_PATTERN_LENGTH, :663-670 */
+		sieve_reset(pn);
+		return 0;
+	}
+	pn->packets_observed++;
+	pn->total_packets_observed++;
+	for (count = 0; count < 64; count++) {
+		if (pn->clock6_candidates[count] > -1 || !(pn->flags & OF_GOT_FIRST)) {
+			int clock = (int)((count + clkn - pn->first_pkt_time) % 64);
+			int uap = do_try_clock(pkt, clock) ? pkt->uap : 0;  /* try_clock returns 0 when the FEC fails */
+			int crc_chk = -1;
+			if (!(pn->flags & OF_GOT_FIRST) || uap == pn->clock6_candidates[count])
+				crc_chk = do_crc_check(pkt, clock);
+			if ((pn->flags & OF_UAP_VALID) && uap != pn->uap)
+				crc_chk = -1;
+			switch (crc_chk) {
+			case -1: case 0:
+				pn->clock6_candidates[count] = -1;
+				break;
+			case 1: case 2:
+				pn->clock6_candidates[count] = (int16_t)uap;
+				first_clock = count;
+				remaining++;
+				break;
+			default:
+				pn->clk_offset = (count - (int)(pn->first_pkt_time & 0x3f)) & 0x3f;
+				pn->uap = (uint8_t)uap;
+				pn->flags |= OF_CLK6_VALID | OF_UAP_VALID;
+				pn->total_packets_observed = 0;
+				return 1;
+			}
+		}
+	}
+	pn->flags |= OF_GOT_FIRST;
+	if (remaining == 1) {
+		pn->clk_offset = (first_clock - (int)(pn->first_pkt_time & 0x3f)) & 0x3f;
+		pn->uap = (uint8_t)pn->clock6_candidates[first_clock];
+		pn->flags |= OF_CLK6_VALID | OF_UAP_VALID;
+		pn->total_packets_observed = 0;
+		return 1;
+	}
+	if (remaining == 0) sieve_reset(pn);
+	return 0;
+}
+
+void orc_uap_sieve(const char *stream, int64_t stream_length, const btbb_b200_pkt_in *pkts, int64_t n_pkts,
+		   const int64_t *group_start, int64_t n_groups, btbb_b200_sieve *states, int8_t *rv)
+{
+	static __thread opkt pkt;
+	int64_t g, p;
+	(void)n_pkts;
+	for (g = 0; g < n_groups; g++) {
+		btbb_b200_sieve *pn = &states[g];
+		for (p = group_start[g]; p < group_start[g + 1]; p++) {
+			const btbb_b200_pkt_in *in = &pkts[p];
+			int length = in->length > 3125 ? 3125 : in->length, r = BTBB_B200_SIEVE_NOT_CALLED;
+			if (in->offset < 0 || in->offset >= stream_length) length = 0;
+			else if (in->offset + length > stream_length) length = (int)(stream_length - in->offset);
+			if (length < 0) length = 0;
+			opkt_load(&pkt, length > 0 ? stream + in->offset : stream, length, in->whitened);
+			sieve_channel_seen(pn, in->reserved & 0xff);
+			if (orc_header_present(pkt.sym, pkt.length) && !(pn->flags & OF_UAP_VALID))
+				r = sieve_uap_from_header(&pkt, in->clkn, in->reserved & 0xff, pn);
+			if (rv) rv[p] = (int8_t)r;
+		}
+	}
+}
+

@@ -41,4 +41,6 @@ void     orc_decode_one(const char *symbols, int length, uint32_t clkn, uint8_t 
 			int whitened, btbb_b200_decoded *out);
 void     orc_try_clock_one(const char *symbols, int length, int clock, int whitened,
 			   btbb_b200_decoded *out);
+void     orc_uap_sieve(const char *stream, int64_t stream_length, const btbb_b200_pkt_in *pkts, int64_t n_pkts,
+		       const int64_t *group_start, int64_t n_groups, btbb_b200_sieve *states, int8_t *rv);
 #endif

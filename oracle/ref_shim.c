@@ -192,3 +192,67 @@ int ref_header_present(char *symbols, int length)
 	btbb_packet_unref(p);
 	return r;
 }
+
+/* ---- UAP / CLK1-6 discovery: the reference's own btbb_uap_from_header (bluetooth_piconet.c,
+ * compiled as a second translation unit by the Makefile), driven the way btbb_process_packet
+ * drives it in survey mode (:851-858) but on a piconet object we own, so that its state can be
+ * carried in and out.  Record layouts as in include/btbb_b200.h. ---- */
+#include <unistd.h>
+#include <fcntl.h>
+#include "bluetooth_piconet.h"
+
+typedef struct {
+	int64_t offset; int32_t length; uint32_t clkn; uint8_t uap, whitened, type, pad; uint32_t reserved;
+} ref_pkt_in;
+typedef struct {
+	uint32_t flags, first_pkt_time; int32_t clk_offset, packets_observed, total_packets_observed;
+	uint8_t uap, used_channels, afh_map[10]; int16_t clock6_candidates[64];
+} ref_sieve;
+
+void ref_uap_sieve(char *stream, int64_t stream_length, const ref_pkt_in *pkts, int64_t n_pkts,
+		   const int64_t *group_start, int64_t n_groups, ref_sieve *states, int8_t *rv)
+{
+	int64_t g, p;
+	int i, saved, devnull;
+	static char zero[1];
+	(void)n_pkts;
+	fflush(stdout);                    /* btbb_uap_from_header prints its findings */
+	saved = dup(1);
+	devnull = open("/dev/null", O_WRONLY);
+	dup2(devnull, 1);
+	for (g = 0; g < n_groups; g++) {
+		btbb_piconet *pn = btbb_piconet_new();
+		ref_sieve *st = &states[g];
+		pn->flags = st->flags; pn->first_pkt_time = st->first_pkt_time; pn->clk_offset = st->clk_offset;
+		pn->packets_observed = st->packets_observed; pn->total_packets_observed = st->total_packets_observed;
+		pn->UAP = st->uap; pn->used_channels = st->used_channels;
+		for (i = 0; i < 10; i++) pn->afh_map[i] = st->afh_map[i];
+		for (i = 0; i < 64; i++) pn->clock6_candidates[i] = st->clock6_candidates[i];
+		for (p = group_start[g]; p < group_start[g + 1]; p++) {
+			const ref_pkt_in *in = &pkts[p];
+			btbb_packet *pkt = btbb_packet_new();
+			int length = in->length > 3125 ? 3125 : in->length, r = -2;
+			if (in->offset < 0 || in->offset >= stream_length) length = 0;
+			else if (in->offset + length > stream_length) length = (int)(stream_length - in->offset);
+			if (length < 0) length = 0;
+			btbb_packet_set_flag(pkt, BTBB_WHITENED, in->whitened);
+			btbb_packet_set_data(pkt, length > 0 ? stream + in->offset : zero, length, (uint8_t)(in->reserved & 0xff), 0);
+			pkt->clkn = in->clkn;              /* as stored, i.e. after btbb_packet_set_data's >> 1 */
+			btbb_piconet_set_channel_seen(pn, pkt->channel);
+			if (btbb_header_present(pkt) && !btbb_piconet_get_flag(pn, BTBB_UAP_VALID))
+				r = btbb_uap_from_header(pkt, pn);
+			if (rv) rv[p] = (int8_t)r;
+			btbb_packet_unref(pkt);
+		}
+		st->flags = pn->flags; st->first_pkt_time = pn->first_pkt_time; st->clk_offset = pn->clk_offset;
+		st->packets_observed = pn->packets_observed; st->total_packets_observed = pn->total_packets_observed;
+		st->uap = pn->UAP; st->used_channels = pn->used_channels;
+		for (i = 0; i < 10; i++) st->afh_map[i] = pn->afh_map[i];
+		for (i = 0; i < 64; i++) st->clock6_candidates[i] = (int16_t)pn->clock6_candidates[i];
+		btbb_piconet_unref(pn);
+	}
+	fflush(stdout);
+	dup2(saved, 1);
+	close(saved); close(devnull);
+}
+

@@ -163,7 +163,27 @@ def gen_noise_types():
             "rv_hist": {str(k): int(v) for k, v in zip(*np.unique(recs["rv"], return_counts=True))}}
 
 
+def gen_sieve():
+    """Digests of the reference's btbb_uap_from_header results (oracle/_ref) on the sieve cases of
+    tests/test_sieve.py -> tests/golden/sieve.json."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import test_sieve
+    R = util.ref()
+    out = {}
+    for name, kw in sorted(test_sieve.CASES.items()):
+        stream, pkts, gs, laps, truth = util.sieve_case(**kw)
+        st, rv = util.sieve_run(R, "ref", stream, pkts, gs)
+        out[name] = {"shape": [len(pkts), len(gs) - 1], "sha256": [util.digest(st), util.digest(rv)],
+                     "piconets_resolved": int(((st["flags"] >> 2) & 1).sum()),
+                     "calls": int((rv >= 0).sum()), "returned_1": int((rv == 1).sum())}
+    json.dump(out, open(os.path.join(HERE, "sieve.json"), "w"), indent=1)
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sieve":
+        print(json.dumps(gen_sieve()))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "find":
         print(json.dumps(gen_find(int(sys.argv[2]))))
         sys.exit(0)
@@ -175,4 +195,5 @@ if __name__ == "__main__":
     json.dump(gen_primitives(), open(os.path.join(HERE, "primitives.json"), "w"), indent=0)
     json.dump(gen_decode(), open(os.path.join(HERE, "decode.json"), "w"), indent=0)
     json.dump(gen_noise_types(), open(os.path.join(HERE, "noise_types.json"), "w"), indent=0)
+    gen_sieve()
     print("golden fixtures written to", HERE)

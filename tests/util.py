@@ -47,6 +47,8 @@ def oracle():
         L.orc_decode_one.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.orc_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_header_present.argtypes = [C.c_void_p, C.c_int]
+        L.orc_uap_sieve.restype = None
+        L.orc_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         _oracle = L
     return _oracle
 
@@ -77,6 +79,8 @@ def ref():
         L.ref_decode_one.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.ref_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_header_present.argtypes = [C.c_void_p, C.c_int]
+        L.ref_uap_sieve.restype = None
+        L.ref_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         _ref = L
     return _ref
 
@@ -130,3 +134,50 @@ def plant_syncwords(stream, rng, count, max_errors, laps=None):
         stream[p:p + 64] = [(sw >> i) & 1 for i in range(64)]
         placed.append((p, lap, ne))
     return placed
+
+
+def sieve_case(n_slots=600, stride=4000, n_laps=12, ber=0.0, seed=B.DEFAULT_SEED, mix=("ID", "DM1", "DH1", "DM3", "FHS", "HV1"),
+               clk_step=1, coherent=True, repeat_first=0):
+    """A piconet-coherent synthetic capture plus the sieve's inputs: the stream, the packets
+    grouped by LAP in arrival order (CLKN = slot * clk_step, channel = slot % 79), the group
+    boundaries and the ground truth {lap: (uap, clk6 of slot 0)}."""
+    n = n_slots * stride
+    cfg = B.synth_cfg(n, stride=stride, n_laps=n_laps, ber=ber, mix=mix, seed=seed, piconets=coherent)
+    stream = B.synth_host(cfg)
+    by_lap, truth = {}, {}
+    for slot in range(n_slots):
+        p = B.planted(cfg, slot)
+        if p.offset + p.n_symbols > n:
+            continue
+        by_lap.setdefault(p.lap, []).append((slot, p))
+        truth[p.lap] = (p.uap, (p.clk6 - slot) & 63)
+    laps = sorted(by_lap)
+    pkts = np.zeros(sum(len(v) for v in by_lap.values()), dtype=B.PKTIN_DTYPE)
+    gs, i = [0], 0
+    for lap in laps:
+        for slot, p in by_lap[lap]:
+            pkts[i]["offset"], pkts[i]["length"] = p.offset, min(3125, n - p.offset)
+            pkts[i]["clkn"], pkts[i]["whitened"], pkts[i]["reserved"] = (slot * clk_step) & 0xFFFFFFFF, 1, slot % 79
+            i += 1
+        gs.append(i)
+    if repeat_first:
+        # every piconet sees its first header-bearing packet again and again at the same CLKN: no
+        # candidate is ever eliminated, which runs into the reference's 1000-packet limit
+        rep, gs2 = [], [0]
+        for g in range(len(laps)):
+            grp = pkts[gs[g]:gs[g + 1]]
+            pick = next((q for q in grp if q["length"] >= 400), grp[0])
+            rep.append(np.repeat(pick[None], repeat_first))
+            gs2.append(gs2[-1] + repeat_first)
+        pkts, gs = np.concatenate(rep), gs2
+    return stream, pkts, np.array(gs, dtype=np.int64), laps, truth
+
+
+def sieve_run(L, prefix, stream, pkts, gs, states=None):
+    """Run an oracle-like library's sieve; returns (states, rv)."""
+    st = np.zeros(len(gs) - 1, dtype=B.SIEVE_DTYPE) if states is None else states.copy()
+    rv = np.zeros(len(pkts), dtype=np.int8)
+    getattr(L, prefix + "_uap_sieve")(stream.ctypes.data, len(stream), pkts.ctypes.data, len(pkts),
+                                      gs.ctypes.data, len(st), st.ctypes.data, rv.ctypes.data)
+    return st, rv
+
