@@ -56,6 +56,61 @@ for mode, name in ((1, "find_ac + 64-clock try_clock/crc_check sweep"), (0, "fin
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     res[name] = {"ms": ms, "packets": int(cnt), "packets_per_s": cnt / (ms / 1e3), "gbit_s": n / (ms / 1e3) / 1e9}
+# ---- UAP / CLK1-6 discovery on a piconet-coherent capture: find_ac -> group hits by LAP
+# -> btbb_b200_uap_sieve_dev.  CLKN of a packet = its 4096-symbol slot index, channel = slot % 79. ----
+cfg2 = B.synth_cfg(n + 63, stride=BLK, ber=0.001, mix=("DM1", "DM3", "DH1", "FHS", "HV1"), piconets=True)
+B.check(lib.btbb_b200_synth_dev(C.byref(cfg2), d.data_ptr(), 0)); torch.cuda.synchronize()
+
+
+def sieve_chain():
+    cnt, rc = ctx.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, k=2, stream=st)
+    h = d_hits[:cnt]
+    off = h.view(torch.int64)[:, 0]
+    lap = h.view(torch.int32)[:, 2].to(torch.int64) & 0xffffff
+    order = torch.sort(lap, stable=True).indices                     # group by LAP, arrival order kept
+    off, lap = off[order], lap[order]
+    laps, counts = torch.unique_consecutive(lap, return_counts=True)
+    gs = torch.zeros(len(laps) + 1, dtype=torch.int64, device="cuda")
+    gs[1:] = torch.cumsum(counts, 0)
+    pk = torch.zeros((cnt, 24), dtype=torch.uint8, device="cuda")
+    pk.view(torch.int64)[:, 0] = off
+    slot = off // BLK
+    pk.view(torch.int32)[:, 2] = torch.clamp((slot + 1) * BLK - off, max=3125).to(torch.int32)
+    pk.view(torch.int32)[:, 3] = slot.to(torch.int32)                 # clkn
+    pk[:, 17] = 1
+    pk.view(torch.int32)[:, 5] = (slot % 79).to(torch.int32)          # channel in `reserved`
+    states = torch.zeros((len(laps), 160), dtype=torch.uint8, device="cuda")
+    rv = torch.zeros(cnt, dtype=torch.int8, device="cuda")
+    B.check(lib.btbb_b200_uap_sieve_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, gs.data_ptr(), len(laps),
+                                         states.data_ptr(), rv.data_ptr(), st))
+    return cnt, pk, gs, laps, states, rv
+
+
+for _ in range(2):
+    sieve_chain()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    cnt, pk, gs, laps, states, rv = sieve_chain()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.iters
+stn = states.cpu().numpy().reshape(-1).view(B.SIEVE_DTYPE)
+res["find_ac + UAP/CLK1-6 sieve (btbb_uap_from_header per piconet)"] = {
+    "ms": ms, "packets": int(cnt), "piconets": int(len(laps)), "piconets_resolved": int(((stn["flags"] >> 2) & 1).sum()),
+    "packets_per_s": cnt / (ms / 1e3), "gbit_s": n / (ms / 1e3) / 1e9}
+# parity of the whole sieve result against the oracle, and the reference C path's time for the same packets
+s_host = d.cpu().numpy()
+pk_h = pk.cpu().numpy().reshape(-1).view(B.PKTIN_DTYPE)
+gs_h = gs.cpu().numpy()
+t0 = time.time()
+want_st, want_rv = util.sieve_run(util.ref() if util.have_ref() else util.oracle(), "ref" if util.have_ref() else "orc", s_host, pk_h, gs_h)
+t_cpu = time.time() - t0
+res["sieve_parity"] = {"states_match": bool(want_st.tobytes() == stn.tobytes()), "rv_match": bool(want_rv.tobytes() == rv.cpu().numpy().tobytes()),
+                       "cpu_kind": "reference" if util.have_ref() else "port", "cpu_seconds_same_packets_1_thread": round(t_cpu, 3)}
+del s_host
+B.check(lib.btbb_b200_synth_dev(C.byref(cfg), d.data_ptr(), 0)); torch.cuda.synchronize()
+
 # parity sample: first 300 hits, 64 clocks each, against the oracle
 cnt, pk, out = chain(1)
 torch.cuda.synchronize()
