@@ -71,6 +71,9 @@ struct btbb_b200_ctx {
 	uint16_t *d_sieve_tc;        /* UAP sieve: (packet, clock) table, 64 words per packet */
 	uint8_t *d_sieve_present;    /* UAP sieve: btbb_header_present per packet */
 	int64_t sieve_cap;           /* packets the two buffers hold */
+	int64_t *d_sieve_idx;        /* UAP sieve: packets of the current round (sieve_cap entries) */
+	int64_t *d_sieve_cur;        /* UAP sieve: per-piconet cursor, then one 64-bit counter */
+	int64_t sieve_groups_cap;
 };
 
 int btbb_b200_set_error(int code, const char *msg);
@@ -101,7 +104,8 @@ int bt_sort_passes(int64_t span);
 
 /* decode.cu */
 int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
-			  const btbb_b200_pkt_in *d_pkts, int64_t n, uint16_t *d_tc, cudaStream_t st);
+			  const btbb_b200_pkt_in *d_pkts, const int64_t *d_idx, const unsigned long long *d_n,
+			  int64_t n_max, uint16_t *d_tc, cudaStream_t st);
 
 /* host_pack.cpp */
 extern "C" void bt_pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out);

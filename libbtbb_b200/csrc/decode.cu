@@ -335,7 +335,8 @@ __device__ __forceinline__ bool fec23_block(uint32_t cw15, const uint8_t *col, u
 
 __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const uint8_t *stream, int64_t stream_len,
 							     const btbb_b200_pkt_in *pkts, int64_t n, int mode,
-							     btbb_b200_decoded *out, uint16_t *tc16)
+							     btbb_b200_decoded *out, uint16_t *tc16,
+							     const int64_t *idx, const unsigned long long *n_dev)
 {
 	__shared__ warp_smem s_w[WARPS];
 	__shared__ uint32_t s_wseq[13];
@@ -350,7 +351,11 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const uint8_t *strea
 
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	warp_smem &ws = s_w[wid];
-	for (int64_t p = (int64_t)blockIdx.x * WARPS + wid; p < n; p += (int64_t)gridDim.x * WARPS) {
+	/* idx / n_dev (the UAP sieve's rounds, sieve.cu): work item i is packet idx[i], and the number
+	 * of items is read from device memory */
+	if (n_dev) n = (int64_t)*n_dev;
+	for (int64_t it = (int64_t)blockIdx.x * WARPS + wid; it < n; it += (int64_t)gridDim.x * WARPS) {
+		const int64_t p = idx ? idx[it] : it;
 		const btbb_b200_pkt_in in = pkts[p];
 		int length = in.length;
 		if (length > BT_MAX_SYMBOLS) length = BT_MAX_SYMBOLS;       /* btbb_packet_set_data :472 */
@@ -535,24 +540,27 @@ extern "C" int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream,
 	int64_t blocks = (n + WARPS - 1) / WARPS;
 	int64_t cap = (int64_t)ctx->sm_count * 16;
 	if (blocks > cap) blocks = cap;
-	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, (cudaStream_t)cuda_stream>>>(d_stream, stream_length, d_pkts, n, mode, d_out, NULL);
+	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, (cudaStream_t)cuda_stream>>>(d_stream, stream_length, d_pkts, n, mode, d_out, NULL, NULL, NULL);
 	BT_CUDA_TRY(cudaGetLastError());
 	return BTBB_B200_OK;
 }
 
-/* try_clock + crc_check for CLK1-6 = 0..63 of n packets (bluetooth_piconet.c:675-689), results
- * as one 16-bit word per (packet, clock): the UAP try_clock returned in the low byte, the
- * crc_check class above it (0, 1, 2 as returned; 3 = 10; 4 = 1000) */
+/* try_clock + crc_check for CLK1-6 = 0..63 (bluetooth_piconet.c:675-689) of the packets listed in
+ * d_idx[0 .. *d_n) (at most n_max of them), results as one 16-bit word per (packet, clock) at
+ * d_tc[64 * packet + clock]: the UAP try_clock returned in the low byte, the crc_check class above
+ * it (0, 1, 2 as returned; 3 = 10; 4 = 1000) */
 int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
-			  const btbb_b200_pkt_in *d_pkts, int64_t n, uint16_t *d_tc, cudaStream_t st)
+			  const btbb_b200_pkt_in *d_pkts, const int64_t *d_idx, const unsigned long long *d_n,
+			  int64_t n_max, uint16_t *d_tc, cudaStream_t st)
 {
 	int rc = upload_dec_tables(ctx->device);
 	if (rc) return rc;
-	if (n == 0) return BTBB_B200_OK;
-	int64_t blocks = (n + WARPS - 1) / WARPS;
+	if (n_max == 0) return BTBB_B200_OK;
+	int64_t blocks = (n_max + WARPS - 1) / WARPS;
 	int64_t cap = (int64_t)ctx->sm_count * 16;
 	if (blocks > cap) blocks = cap;
-	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, st>>>(d_stream, stream_length, d_pkts, n, BTBB_B200_MODE_TRY_CLOCKS, NULL, d_tc);
+	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, st>>>(d_stream, stream_length, d_pkts, n_max, BTBB_B200_MODE_TRY_CLOCKS,
+							      NULL, d_tc, d_idx, d_n);
 	BT_CUDA_TRY(cudaGetLastError());
 	return BTBB_B200_OK;
 }

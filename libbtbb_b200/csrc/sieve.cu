@@ -15,7 +15,9 @@
  * trivially parallel across piconets: one warp per piconet walks its packets, lane L owning
  * candidates L and L + 32, with ballots for "first success in candidate order" (the reference
  * returns from inside its loop, so later candidates must stay untouched) and for the
- * survivor count.
+ * survivor count.  Because the reference stops looking at a piconet once its UAP is known, the
+ * work is done in rounds of 4, 32, 256, ... packets per piconet, and the 64-clock table is only
+ * computed for the packets of piconets that are still unresolved.
  */
 #include <string.h>
 #include "bt_math.h"
@@ -35,13 +37,45 @@ __device__ __forceinline__ void sieve_reset(uint32_t &flags, int &pobs)
 	pobs = 0;
 }
 
-__global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts, const uint8_t *present,
-						    const uint16_t *tc, const int64_t *group_start, int64_t n_groups,
-						    btbb_b200_sieve *states, int8_t *rv_out)
+/* cur[g] = first packet of piconet g that has not been handled yet */
+__global__ void sieve_init_kernel(const int64_t *group_start, int64_t n_groups, int64_t *cur)
+{
+	const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < n_groups) cur[g] = group_start[g];
+}
+
+/* The packets the next round needs the 64-clock table for: the next `window` packets of every
+ * piconet whose UAP is still unknown.  One warp per piconet; *counter is the list length. */
+__global__ void __launch_bounds__(128) sieve_list_kernel(const int64_t *group_start, int64_t n_groups,
+							 const btbb_b200_sieve *states, const int64_t *cur, int64_t window,
+							 int64_t *idx, unsigned long long *counter)
 {
 	const int lane = threadIdx.x & 31;
 	const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if (g >= n_groups) return;
+	const int64_t c = cur[g], end = group_start[g + 1];
+	if (c >= end || (states[g].flags & F_UAP_VALID)) return;
+	const int64_t cnt = end - c < window ? end - c : window;
+	unsigned long long base = 0;
+	if (lane == 0) base = atomicAdd(counter, (unsigned long long)cnt);
+	base = __shfl_sync(0xffffffffu, base, 0);
+	for (int64_t i = lane; i < cnt; i += 32) idx[base + i] = c + i;
+}
+
+/* One round: every piconet with packets left takes up to `window` more of them through
+ * btbb_process_packet's survey branch; once its UAP is known (now or on entry) the rest of its
+ * packets only mark their channels (btbb_piconet_set_channel_seen) and report "not called". */
+__global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts, const uint8_t *present,
+						    const uint16_t *tc, const int64_t *group_start, int64_t n_groups,
+						    btbb_b200_sieve *states, int8_t *rv_out, int64_t *cur, int64_t window)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (g >= n_groups) return;
+	const int64_t end = group_start[g + 1];
+	int64_t p = cur[g];
+	if (p >= end) return;
+	const int64_t limit = end - p < window ? end : p + window;
 	btbb_b200_sieve *st = &states[g];
 	uint32_t flags = st->flags, first = st->first_pkt_time;
 	int clk_offset = st->clk_offset, pobs = st->packets_observed, total = st->total_packets_observed;
@@ -49,7 +83,26 @@ __global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts
 	uint32_t afh = lane < 10 ? st->afh_map[lane] : 0;
 	int c0 = st->clock6_candidates[lane], c1 = st->clock6_candidates[lane + 32];
 
-	for (int64_t p = group_start[g]; p < group_start[g + 1]; p++) {
+	while (p < end) {
+		if (flags & F_UAP_VALID) {
+			/* the rest of the piconet's packets, 32 at a time: channels seen, nothing called */
+			uint32_t m0 = 0, m1 = 0, m2 = 0;
+			for (int64_t q = p + lane; q < end; q += 32) {
+				const uint32_t channel = pkts[q].reserved & 0xffu;
+				if (channel < 32) m0 |= 1u << channel;
+				else if (channel < 64) m1 |= 1u << (channel - 32);
+				else if (channel < 80) m2 |= 1u << (channel - 64);
+				if (rv_out) rv_out[q] = (int8_t)BTBB_B200_SIEVE_NOT_CALLED;
+			}
+			m0 = __reduce_or_sync(0xffffffffu, m0); m1 = __reduce_or_sync(0xffffffffu, m1); m2 = __reduce_or_sync(0xffffffffu, m2);
+			const uint32_t mine = lane < 4 ? (m0 >> (8 * lane)) & 0xff : lane < 8 ? (m1 >> (8 * (lane - 4))) & 0xff
+					     : lane < 10 ? (m2 >> (8 * (lane - 8))) & 0xff : 0;
+			used += __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mine & ~afh));
+			afh |= mine;
+			p = end;
+			break;
+		}
+		if (p >= limit) break;
 		const uint32_t clkn = pkts[p].clkn, channel = pkts[p].reserved & 0xffu;
 		/* btbb_piconet_set_channel_seen (:851-855 and :661) */
 		if (channel < 80) {
@@ -60,7 +113,7 @@ __global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts
 			}
 		}
 		int rv = BTBB_B200_SIEVE_NOT_CALLED;
-		if (present[p] && !(flags & F_UAP_VALID)) {
+		if (present[p]) {
 			const bool got_first = (flags & F_GOT_FIRST) != 0;
 			if (!got_first) first = clkn;
 			if (pobs >= MAX_PATTERN_LENGTH) {          /* "More hops than we can remember" (:665-671) */
@@ -68,7 +121,6 @@ __global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts
 				rv = 0;
 			} else {
 				pobs++; total++;
-				const bool uap_valid = (flags & F_UAP_VALID) != 0;
 				/* candidate `count` implies clock (count + clkn - first) % 64 for this packet (:681) */
 				const uint32_t e0 = tc[p * 64 + ((lane + clkn - first) & 63u)];
 				const uint32_t e1 = tc[p * 64 + ((lane + 32 + clkn - first) & 63u)];
@@ -77,8 +129,8 @@ __global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts
 				int k0 = -1, k1 = -1;             /* crc_chk: -1 mismatch, else the class of crc_check's value */
 				if (!got_first || u0 == c0) k0 = (int)(e0 >> 8);
 				if (!got_first || u1 == c1) k1 = (int)(e1 >> 8);
-				if (uap_valid && (uint32_t)u0 != uap) k0 = -1;
-				if (uap_valid && (uint32_t)u1 != uap) k1 = -1;
+				/* (the reference's "UAP known but different" test, :693-695, cannot fire here:
+				 * survey mode stops calling once the UAP is valid) */
 				const uint32_t s0 = __ballot_sync(0xffffffffu, a0 && k0 >= 3), s1 = __ballot_sync(0xffffffffu, a1 && k1 >= 3);
 				const int winner = s0 ? __ffs(s0) - 1 : s1 ? 32 + __ffs(s1) - 1 : 64;
 				/* every candidate below the winner is updated; the winner and all above are left alone */
@@ -112,6 +164,7 @@ __global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts
 			}
 		}
 		if (rv_out && lane == 0) rv_out[p] = (int8_t)rv;
+		p++;
 	}
 	st->clock6_candidates[lane] = (int16_t)c0;
 	st->clock6_candidates[lane + 32] = (int16_t)c1;
@@ -120,6 +173,7 @@ __global__ void __launch_bounds__(128) sieve_kernel(const btbb_b200_pkt_in *pkts
 		st->flags = flags; st->first_pkt_time = first; st->clk_offset = clk_offset;
 		st->packets_observed = pobs; st->total_packets_observed = total;
 		st->uap = (uint8_t)uap; st->used_channels = (uint8_t)used;
+		cur[g] = p;
 	}
 }
 
@@ -139,18 +193,45 @@ extern "C" int btbb_b200_uap_sieve_dev(btbb_b200_ctx *ctx, const uint8_t *d_stre
 	if (n_pkts > ctx->sieve_cap) {
 		if (ctx->d_sieve_tc) cudaFree(ctx->d_sieve_tc);
 		if (ctx->d_sieve_present) cudaFree(ctx->d_sieve_present);
-		ctx->d_sieve_tc = NULL; ctx->d_sieve_present = NULL; ctx->sieve_cap = 0;
+		if (ctx->d_sieve_idx) cudaFree(ctx->d_sieve_idx);
+		ctx->d_sieve_tc = NULL; ctx->d_sieve_present = NULL; ctx->d_sieve_idx = NULL; ctx->sieve_cap = 0;
 		const int64_t cap = n_pkts < 4096 ? 4096 : n_pkts;
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_sieve_tc, (size_t)cap * 64 * sizeof(uint16_t)));
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_sieve_present, (size_t)cap));
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_sieve_idx, (size_t)cap * sizeof(int64_t)));
 		ctx->sieve_cap = cap;
 	}
+	if (n_groups > ctx->sieve_groups_cap) {
+		if (ctx->d_sieve_cur) cudaFree(ctx->d_sieve_cur);
+		ctx->d_sieve_cur = NULL; ctx->sieve_groups_cap = 0;
+		const int64_t cap = n_groups < 1024 ? 1024 : n_groups;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_sieve_cur, (size_t)(cap + 1) * sizeof(int64_t)));
+		ctx->sieve_groups_cap = cap;
+	}
+	int64_t *cur = ctx->d_sieve_cur;
+	unsigned long long *counter = reinterpret_cast<unsigned long long *>(ctx->d_sieve_cur + ctx->sieve_groups_cap);
 	int rc = btbb_b200_header_present_dev(ctx, d_stream, stream_length, d_pkts, n_pkts, ctx->d_sieve_present, cuda_stream);
-	if (!rc) rc = bt_try_clocks_compact(ctx, d_stream, stream_length, d_pkts, n_pkts, ctx->d_sieve_tc, st);
 	if (rc) return rc;
 	const int wpb = 4;
-	sieve_kernel<<<(unsigned)((n_groups + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_pkts, ctx->d_sieve_present, ctx->d_sieve_tc,
-										     d_group_start, n_groups, d_states, d_rv);
+	const unsigned gblocks = (unsigned)((n_groups + wpb - 1) / wpb);
+	sieve_init_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(d_group_start, n_groups, cur);
+	/* Rounds of 4, 32, 256, ... packets per piconet: the reference stops working on a piconet as
+	 * soon as its UAP is known (typically after one or two packets with a CRC), so the 64-clock
+	 * table is only computed for the packets a round can still need.  No host round trip: the
+	 * list length stays on the device, and a round with nothing left is three empty launches. */
+	int64_t done = 0;
+	for (int64_t window = 4; done < n_pkts || window == 4; window *= 8) {
+		BT_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(*counter), st));
+		sieve_list_kernel<<<gblocks, wpb * 32, 0, st>>>(d_group_start, n_groups, d_states, cur, window, ctx->d_sieve_idx, counter);
+		int64_t n_max = n_pkts - done;
+		if (n_groups < ((int64_t)1 << 40) / window && n_groups * window < n_max) n_max = n_groups * window;
+		rc = bt_try_clocks_compact(ctx, d_stream, stream_length, d_pkts, ctx->d_sieve_idx, counter, n_max, ctx->d_sieve_tc, st);
+		if (rc) return rc;
+		sieve_kernel<<<gblocks, wpb * 32, 0, st>>>(d_pkts, ctx->d_sieve_present, ctx->d_sieve_tc, d_group_start, n_groups,
+							  d_states, d_rv, cur, window);
+		done += window;        /* every piconet with packets left has now handled at least this many more */
+		if (window > ((int64_t)1 << 40)) break;
+	}
 	BT_CUDA_TRY(cudaGetLastError());
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
 	return BTBB_B200_OK;
