@@ -501,7 +501,9 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	const bool force_v1 = env && !strcmp(env, "v1");
 	if (n <= 0) return BTBB_B200_OK;
 	const bool known = lap != BTBB_B200_LAP_ANY;
-	if ((!known && !ctx->d_map2) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
+	/* tables for 3 errors: only the byte-format v7 kernel has a bulk path (global second-level map) */
+	const bool k3 = !known && !ctx->d_map2 && ctx->d_map7g;
+	if ((!known && !ctx->d_map2 && !(k3 && !packed)) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
 		if (packed) {      /* no bulk kernel for this case: expand to the byte format and take the tile kernel */
 			int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), 0, n + 63, st);
 			if (rc0) return rc0;
@@ -514,9 +516,9 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	 * slots) for packed input.  BTBB_B200_SCAN=v6.. selects the experimental scan_v6.cuh, whose
 	 * windows start one symbol before the aligned data it loads (so it wants at least one symbol
 	 * in front); v3 / v4a.. the older generations, v7 / v7f / .. the v7 variants */
-	const bool use_v6 = !known && !packed && env && !strncmp(env, "v6", 2);
+	const bool use_v6 = !known && !packed && !k3 && env && !strncmp(env, "v6", 2);
 	/* byte-format promiscuous scans run scan_v7.cuh unless an older generation is asked for */
-	const bool use_v7 = !known && !packed && !use_v6 && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3")));
+	const bool use_v7 = k3 || (!known && !packed && !use_v6 && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3"))));
 	const char *env7 = env && !strncmp(env, "v7", 2) ? env : NULL;
 	int64_t al = packed ? 0 : (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
 	if (use_v6 && al == 0) al = 32;
@@ -541,7 +543,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	memset(&xp, 0, sizeof(xp));
 	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
 	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0; xp.stream = packed ? NULL : d_stream;
-	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err;
+	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err; xp.map2g = ctx->d_map7g;
 	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
 	int bulk_warps = 32;
 	if (use_v6 && env && !strncmp(env, "v6w24", 5)) bulk_warps = 24;
@@ -600,7 +602,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		/* developer switch: v7 = multiply windows, v7f = funnel-shift windows; a trailing 'a'
 		 * selects layout<1> (table A by byte permute, 32 KiB map); s4 / s6 = inline slots */
 		v7::args a;
-		const bool ta = !env7 || strchr(env7 + 2, 'a') != NULL;
+		const bool ta = !k3 && (!env7 || strchr(env7 + 2, 'a') != NULL);
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const v3::xparams *)slot;
 		a.m1 = 0xffffffffu; a.c64 = 64u;
@@ -612,6 +614,8 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		else if (env7 && !strcmp(env7, "v7fs6")) kern = v7::scan_promisc_v7<0, 6, 0>;
 		else if (env7 && !strcmp(env7, "v7fas4")) kern = v7::scan_promisc_v7<0, 4, 1>;
 		else if (env7 && !strcmp(env7, "v7fas6")) kern = v7::scan_promisc_v7<0, 6, 1>;
+		/* 3-error tables: the 64 KiB first-level map (12 % of it set) and the global second level */
+		if (k3) kern = env7 && !strcmp(env7, "v7fs6") ? v7::scan_promisc_v7<0, 6, 0, 1> : v7::scan_promisc_v7<0, 5, 0, 1>;
 		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);

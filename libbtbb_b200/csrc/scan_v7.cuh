@@ -165,10 +165,18 @@ __device__ __forceinline__ uint32_t map1_bit(uint32_t sy)
 	const uint32_t rep = mul_lo(lds8o<L::sa_map>(sy >> (32 - L::map_log2)), 0x01010101u);
 	return (rep >> (sy & 31)) & 1u;
 }
-/* second-level map: word = bits 8..19, bit = bits 3..7 */
-template <int TA>
-__device__ __forceinline__ uint32_t map2_bit(uint32_t sy)
+/* second-level map: word = bits 8..19, bit = bits 3..7.  M2G (tables for 3 errors: 68 558
+ * reachable values would fill the 2^17-bit shared map to 41 %): a 2^27-bit map in global memory,
+ * word = bits 10..31, bit = bits 5..9; it is L2-resident (16 MiB) and consulted about 60 times
+ * per strip and warp, by all lanes of a consumer round at once */
+constexpr int M2G_LOG2 = 27;
+template <int TA, int M2G>
+__device__ __forceinline__ uint32_t map2_bit(uint32_t sy, const xparams *xp)
 {
+	if (M2G) {
+		const uint32_t mw = __ldg(xp->map2g + (sy >> 10));
+		return (mw >> ((sy >> 5) & 31)) & 1u;
+	}
 	const uint32_t mw = lds32o<layout<TA>::sa_m2>((sy >> 6) & (uint32_t)((M2_WORDS - 1) * 4));
 	return (mw >> ((sy >> 3) & 31)) & 1u;
 }
@@ -242,18 +250,18 @@ __device__ __forceinline__ void slot7(uint32_t &c, uint32_t &hitm, uint32_t r0, 
 }
 
 /* one queued candidate (or any candidate, from the bit tile): both map levels, then park */
-template <int TA>
+template <int TA, int M2G>
 __device__ __forceinline__ void tile_candidate(const xparams *xp, uint32_t x_sa, uint32_t wa, uint32_t q, uint32_t rel,
 					       uint32_t lane4, uint32_t c64)
 {
 	const uint32_t w0 = lds32o<0>(wa), x1 = lds32o<4>(wa), x2 = lds32o<8>(wa);
 	const uint32_t lo = __funnelshift_r(w0, x1, q), hi = __funnelshift_r(x1, x2, q);
 	const uint32_t sy = fp7<TA>(__funnelshift_r(lo, hi, 1), hi >> 1, lane4, c64);
-	if (map1_bit<TA>(sy) && map2_bit<TA>(sy))
+	if (map1_bit<TA>(sy) && map2_bit<TA, M2G>(sy, xp))
 		park7<TA>(xp, x_sa, rel, lo, hi);
 }
 
-template <int WIN, int NSLOTS, int TA>
+template <int WIN, int NSLOTS, int TA, int M2G = 0>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 {
 	typedef layout<TA> L;
@@ -276,7 +284,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 			sts32((e < 384 ? L::sa_bc + 256 * (e - 128) : L::sa_bc + 128 + 256 * (e - 384)) + 4 * l, v);
 	}
 	for (int i = threadIdx.x; i < (1 << (L::map_log2 - 2)); i += WARPS * 32) sts32(L::sa_map + 4 * i, a.map[i]);
-	for (int i = threadIdx.x; i < M2_WORDS; i += WARPS * 32) sts32(L::sa_m2 + 4 * i, a.map[(1 << (L::map_log2 - 2)) + i]);
+	if (!M2G)
+		for (int i = threadIdx.x; i < M2_WORDS; i += WARPS * 32) sts32(L::sa_m2 + 4 * i, a.map[(1 << (L::map_log2 - 2)) + i]);
 	const uint32_t x_sa = SA_X + wid * X_BYTES;
 	const uint32_t s_sa = L::sa_warp + wid * S_BYTES;
 	const uint32_t q_sa = L::sa_q + wid * QCAP * 2;
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 					while (c) {
 						const uint32_t q = bfind(c);
 						c ^= 1u << q;
-						tile_candidate<TA>(xp, x_sa, my_sa + 128 * k, q, strip_pos + (k * 32 + lane) * 32 + q, lane4, c64);
+						tile_candidate<TA, M2G>(xp, x_sa, my_sa + 128 * k, q, strip_pos + (k * 32 + lane) * 32 + q, lane4, c64);
 					}
 				}
 			} else {
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 				__syncwarp();
 				for (uint32_t i = lane; i < ov; i += 32) {
 					const uint32_t e = lds16o<0>(q_sa + 2 * i);
-					tile_candidate<TA>(xp, x_sa, s_sa + (e >> 5), e, strip_pos + (e >> 7) * 32 + (e & 31), lane4, c64);
+					tile_candidate<TA, M2G>(xp, x_sa, s_sa + (e >> 5), e, strip_pos + (e >> 7) * 32 + (e & 31), lane4, c64);
 				}
 				__syncwarp();
 				if (lane == 0) sts32(qn_sa, 0);

@@ -78,7 +78,7 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
 	ctx->m32 = ctx->m33 = ctx->m0 = 0;
 	ctx->d_lut6 = NULL; ctx->d_map6 = NULL;
-	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL;
+	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL; ctx->d_map7g = NULL;
 	for (int j = 0; j < 25; j++) {
 		if (g_bit_syn[32 + j] & 1) ctx->m0 |= 1u << j;
 		if ((g_bit_syn[32 + j] >> 32) & 1) ctx->m32 |= 1u << j;
@@ -184,41 +184,57 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 			BT_CUDA_TRY(cudaMalloc(&ctx->d_map6, map6.size() * sizeof(uint32_t)));
 			BT_CUDA_TRY(cudaMemcpy(ctx->d_map6, map6.data(), map6.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		}
-		/* v7 (scan_v7.cuh) works on syndrome bits 1..32 like v6: field tables A / B / C over
-		 * codeword bits 34..40 / 41..48 / 49..56, a first-level map addressed by byte (byte =
-		 * value bits 16..31, bit = bits 0..2) and a second-level map over value bits 3..19
-		 * (word = bits 8..19, bit = bits 3..7) */
-		{
-			std::vector<uint32_t> l7;
-			const int fw7[3] = {7, 8, 8};
-			for (int f = 0, pos = 0; f < 3; pos += fw7[f], f++)
-				for (uint32_t v = 0; v < (1u << fw7[f]); v++) {
-					uint64_t sy = 0;
-					for (int j = 0; j < fw7[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + pos + j];
-					l7.push_back((uint32_t)(sy >> 1));
-				}
-			BT_CUDA_TRY(cudaMalloc(&ctx->d_lut7, l7.size() * sizeof(uint32_t)));
-			BT_CUDA_TRY(cudaMemcpy(ctx->d_lut7, l7.data(), l7.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-			/* two sizes of the first-level map: 2^16 bytes (layout<0>) and 2^15 bytes (layout<1>) */
-			for (int variant = 0; variant < 2; variant++) {
-				const int lg = variant ? 15 : 16;
-				const size_t m1_bytes = (size_t)1 << lg;
-				std::vector<uint32_t> map7(m1_bytes / 4 + m2_words, 0u);
-				uint8_t *mb = reinterpret_cast<uint8_t *>(map7.data());
-				uint32_t *m2 = map7.data() + m1_bytes / 4;
-				auto map7_add = [&](uint64_t s34) {
-					for (int c = 0; c < 2; c++) {
-						uint32_t v = (uint32_t)((s34 ^ ctx->cc[c]) >> 1);
-						mb[v >> (32 - lg)] |= (uint8_t)(1u << (v & 7));
-						m2[(v >> 8) & (m2_words - 1)] |= 1u << ((v >> 3) & 31);
-					}
-				};
-				map7_add(0);
-				for (auto &e : ents) map7_add(e.syn);
-				uint32_t **dst = variant ? &ctx->d_map7b : &ctx->d_map7;
-				BT_CUDA_TRY(cudaMalloc(dst, map7.size() * sizeof(uint32_t)));
-				BT_CUDA_TRY(cudaMemcpy(*dst, map7.data(), map7.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	}
+
+	/* v7 (scan_v7.cuh) works on syndrome bits 1..32 like v6: field tables A / B / C over
+	 * codeword bits 34..40 / 41..48 / 49..56, a first-level map addressed by byte (byte = the
+	 * top 16 / 15 value bits, bit = bits 0..2) and a second-level map -- for k <= 2 in shared
+	 * memory over value bits 3..19 (word = bits 8..19, bit = bits 3..7), for k = 3 (68 558
+	 * reachable values) 2^27 bits in global memory (word = bits 10..31, bit = bits 5..9) */
+	if (k <= 3) {
+		const size_t m2_words = (size_t)1 << (17 - 5);
+		std::vector<uint32_t> l7;
+		const int fw7[3] = {7, 8, 8};
+		for (int f = 0, pos = 0; f < 3; pos += fw7[f], f++)
+			for (uint32_t v = 0; v < (1u << fw7[f]); v++) {
+				uint64_t sy = 0;
+				for (int j = 0; j < fw7[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + pos + j];
+				l7.push_back((uint32_t)(sy >> 1));
 			}
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_lut7, l7.size() * sizeof(uint32_t)));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut7, l7.data(), l7.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		/* two sizes of the first-level map: 2^16 bytes (layout<0>) and 2^15 bytes (layout<1>) */
+		for (int variant = 0; variant < 2; variant++) {
+			const int lg = variant ? 15 : 16;
+			const size_t m1_bytes = (size_t)1 << lg;
+			std::vector<uint32_t> map7(m1_bytes / 4 + m2_words, 0u);
+			uint8_t *mb = reinterpret_cast<uint8_t *>(map7.data());
+			uint32_t *m2 = map7.data() + m1_bytes / 4;
+			auto map7_add = [&](uint64_t s34) {
+				for (int c = 0; c < 2; c++) {
+					uint32_t v = (uint32_t)((s34 ^ ctx->cc[c]) >> 1);
+					mb[v >> (32 - lg)] |= (uint8_t)(1u << (v & 7));
+					m2[(v >> 8) & (m2_words - 1)] |= 1u << ((v >> 3) & 31);
+				}
+			};
+			map7_add(0);
+			for (auto &e : ents) map7_add(e.syn);
+			uint32_t **dst = variant ? &ctx->d_map7b : &ctx->d_map7;
+			BT_CUDA_TRY(cudaMalloc(dst, map7.size() * sizeof(uint32_t)));
+			BT_CUDA_TRY(cudaMemcpy(*dst, map7.data(), map7.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+		}
+		if (k == 3) {
+			std::vector<uint32_t> g((size_t)1 << (27 - 5), 0u);
+			auto g_add = [&](uint64_t s34) {
+				for (int c = 0; c < 2; c++) {
+					uint32_t v = (uint32_t)((s34 ^ ctx->cc[c]) >> 1);
+					g[v >> 10] |= 1u << ((v >> 5) & 31);
+				}
+			};
+			g_add(0);
+			for (auto &e : ents) g_add(e.syn);
+			BT_CUDA_TRY(cudaMalloc(&ctx->d_map7g, g.size() * sizeof(uint32_t)));
+			BT_CUDA_TRY(cudaMemcpy(ctx->d_map7g, g.data(), g.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		}
 	}
 
@@ -256,6 +272,8 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_lut7) cudaFree(ctx->d_lut7);
 	if (ctx->d_map7) cudaFree(ctx->d_map7);
 	if (ctx->d_map7b) cudaFree(ctx->d_map7b);
+	if (ctx->d_map7g) cudaFree(ctx->d_map7g);
+	ctx->d_map7g = NULL;
 	ctx->d_lut6 = NULL; ctx->d_map6 = NULL; ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL;
 	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
 	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL; ctx->d_lut2b = NULL; ctx->d_lut3 = NULL;
