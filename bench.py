@@ -156,10 +156,30 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: everything else that writes to fd 1 (NCCL's version
+    banner, library chatter) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -342,7 +362,7 @@ def main():
                            "parallelism": f"contiguous shards x{world}, padded NCCL all-gather of hit records"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * steps,
                 "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -25,6 +25,7 @@ def shard_read_span(n_positions, rank, world, total_symbols):
 
 
 _bufs = {}
+_cap_hint = {}
 
 
 def gather_hits(local_hits, group=None, concat=True):
@@ -34,26 +35,41 @@ def gather_hits(local_hits, group=None, concat=True):
     whose offsets are already global.  Returns (all_hits [n_total, 16], counts list); with
     concat=False the first item is the padded [world, cap, 16] receive buffer instead (rank
     r's records are buf[r, :counts[r]]), which skips one device copy.
-    NCCL has no native allgatherv: one all_gather of the counts, then one all_gather of the
-    records padded to the largest count.  Buffers are cached between calls.
+    NCCL has no native allgatherv, so the exchange is ONE all_gather of fixed-size slots: slot r
+    holds rank r's count (first 8 bytes of a 16-byte header record) followed by its records,
+    padded to a capacity every rank derives the same way -- the largest count seen so far,
+    rounded up.  The capacity is agreed once (one all_gather of the counts on the first call)
+    and re-agreed only when some rank outgrows it; in steady state a call is one collective and
+    one host read of the counts.  Buffers are cached between calls.
     """
     world = dist.get_world_size(group)
     dev = local_hits.device
-    n_local = torch.tensor([local_hits.shape[0]], dtype=torch.int64, device=dev)
-    all_n = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_n, n_local, group=group)
-    counts = all_n.tolist()                        # the one host sync of the exchange
-    cap = max(max(counts), 1)
-    cap = (cap + 65535) // 65536 * 65536           # round up so that the buffers get reused
-    key = (str(dev), world, cap)
-    if key not in _bufs:
-        _bufs.clear()
-        _bufs[key] = (torch.zeros((cap, 16), dtype=torch.uint8, device=dev),
-                      torch.empty((world, cap, 16), dtype=torch.uint8, device=dev))
-    send, recv = _bufs[key]
-    send[: local_hits.shape[0]].copy_(local_hits)
-    dist.all_gather_into_tensor(recv.view(world * cap, 16), send, group=group)
+    n = int(local_hits.shape[0])
+    gkey = (str(dev), world, id(group))
+    while True:
+        cap = _cap_hint.get(gkey)
+        if cap is None:
+            n_local = torch.tensor([n], dtype=torch.int64, device=dev)
+            all_n = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(all_n, n_local, group=group)
+            cap = max(int(all_n.max().item()), 1)
+            cap = (cap + cap // 64 + 4095) // 4096 * 4096      # 1.5 % head room, then a multiple of 4096
+            _cap_hint[gkey] = cap
+        key = (str(dev), world, cap)
+        if key not in _bufs:
+            _bufs.clear()
+            _bufs[key] = (torch.zeros((cap + 1, 16), dtype=torch.uint8, device=dev),
+                          torch.empty((world, cap + 1, 16), dtype=torch.uint8, device=dev))
+        send, recv = _bufs[key]
+        send.view(torch.int64)[0, 0] = n
+        send[1: 1 + min(n, cap)].copy_(local_hits[:cap])
+        dist.all_gather_into_tensor(recv.view(world * (cap + 1), 16), send, group=group)
+        counts = recv.view(torch.int64)[:, 0, 0].tolist()      # the one host sync of the exchange
+        if max(counts) <= cap:
+            break
+        del _cap_hint[gkey]                                    # some rank outgrew the slots: agree on a new size
+    body = recv[:, 1:]
     if not concat:
-        return recv, counts
-    out = torch.cat([recv[r, :c] for r, c in enumerate(counts)], dim=0)
+        return body, counts
+    out = torch.cat([body[r, :c] for r, c in enumerate(counts)], dim=0)
     return out, counts
