@@ -502,7 +502,8 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	if (n <= 0) return BTBB_B200_OK;
 	const bool known = lap != BTBB_B200_LAP_ANY;
 	/* tables for 3 errors: only the byte-format v7 kernel has a bulk path (global second-level map) */
-	const bool k3 = !known && !ctx->d_map2 && ctx->d_map7g;
+	const bool k3 = !known && !ctx->d_map2 && ctx->d_map7g;      /* 3, 4 or 5 */
+	const bool k45 = k3 && ctx->table_k >= 4;
 	if ((!known && !ctx->d_map2 && !(k3 && !packed)) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
 		if (packed) {      /* no bulk kernel for this case: expand to the byte format and take the tile kernel */
 			int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), 0, n + 63, st);
@@ -606,6 +607,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const v3::xparams *)slot;
 		a.m1 = 0xffffffffu; a.c64 = 64u;
+		a.map1g = reinterpret_cast<const uint8_t *>(ctx->d_map7g); a.m1g_shift = 32 - (ctx->map7g_log2 - 3);
 		void (*kern)(const v7::args) = v7::scan_promisc_v7<0, 5, 1>;       /* shipped */
 		if (env7 && !strcmp(env7, "v7")) kern = v7::scan_promisc_v7<1, 5, 0>;
 		else if (env7 && !strcmp(env7, "v7f")) kern = v7::scan_promisc_v7<0, 5, 0>;
@@ -616,6 +618,8 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		else if (env7 && !strcmp(env7, "v7fas6")) kern = v7::scan_promisc_v7<0, 6, 1>;
 		/* 3-error tables: the 64 KiB first-level map (12 % of it set) and the global second level */
 		if (k3) kern = env7 && !strcmp(env7, "v7fs6") ? v7::scan_promisc_v7<0, 6, 0, 1> : v7::scan_promisc_v7<0, 5, 0, 1>;
+		/* 4 / 5-error tables: first level in global memory, positives straight to the exact test */
+		if (k45) kern = v7::scan_promisc_v7<0, 5, 0, 2>;
 		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);

@@ -88,6 +88,8 @@ struct args {
 	const xparams *xp;
 	uint32_t m1;             /* 0xffffffff, opaque to the compiler: a * m1 + b is a - b on the FMA pipe */
 	uint32_t c64;            /* 64, likewise: (x & 0xfe) * c64 + 4 lane stays an IMAD */
+	const uint8_t *map1g;    /* M2G = 2 (tables for 4 / 5 errors): first-level map in global memory, */
+	uint32_t m1g_shift;      /*   byte = value >> m1g_shift, bit = value & 7 */
 };
 
 __device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b)
@@ -157,6 +159,18 @@ __device__ __forceinline__ uint32_t fp7(uint32_t lo1, uint32_t hi1, uint32_t lan
 	return lo1 ^ ta ^ tb ^ tc;
 }
 
+/* M2G = 2: with 10^6 (4 errors) or 10^7 (5 errors) reachable values no map that fits in shared
+ * memory filters anything, so the first level itself lives in global memory -- 2^27 / 2^29 bits,
+ * L2-resident next to the stream, whose loads do not allocate in L1 -- and every real candidate
+ * costs one 32-byte L2 sector.  live == 0 (a lane without a candidate) skips the load. */
+struct gmap { const uint8_t *p; uint32_t shift; };
+__device__ __forceinline__ uint32_t map1g_bit(uint32_t sy, gmap m, uint32_t live)
+{
+	uint32_t v = 0;
+	if (live) asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(m.p + (sy >> m.shift)));
+	return (v >> (sy & 7)) & 1u;
+}
+
 /* first-level map: byte = the top map_log2 bits of the value, bit = (value & 7); returns 0 / 1 */
 template <int TA>
 __device__ __forceinline__ uint32_t map1_bit(uint32_t sy)
@@ -173,6 +187,7 @@ constexpr int M2G_LOG2 = 27;
 template <int TA, int M2G>
 __device__ __forceinline__ uint32_t map2_bit(uint32_t sy, const xparams *xp)
 {
+	if (M2G == 2) return 1u;                 /* straight to the exact test (a few per strip) */
 	if (M2G) {
 		const uint32_t mw = __ldg(xp->map2g + (sy >> 10));
 		return (mw >> ((sy >> 5) & 31)) & 1u;
@@ -228,9 +243,9 @@ __device__ __noinline__ void park7(const xparams *xp, uint32_t x_sa, uint32_t re
  * words 0..2 of W >> 1 (W = w0 | w1 << 32 | w2 << 64).  A lane without a candidate runs the
  * same instructions on an all-zero (WIN = 1) or dummy (WIN = 0) window and adds nothing: its
  * b is 0.  A first-level positive sets the candidate's bit in hitm (same bit order as c). */
-template <int WIN, int TA>
+template <int WIN, int TA, int M2G>
 __device__ __forceinline__ void slot7(uint32_t &c, uint32_t &hitm, uint32_t r0, uint32_t r1, uint32_t r2,
-				      uint32_t lane4, uint32_t m1, uint32_t c64)
+				      uint32_t lane4, uint32_t m1, uint32_t c64, gmap gm)
 {
 	uint32_t b, lo1, hi1;
 	if (WIN == 1) {
@@ -246,18 +261,19 @@ __device__ __forceinline__ void slot7(uint32_t &c, uint32_t &hitm, uint32_t r0, 
 		lo1 = __funnelshift_r(r0, r1, q);
 		hi1 = __funnelshift_r(r1, r2, q);
 	}
-	hitm = mad_lo(map1_bit<TA>(fp7<TA>(lo1, hi1, lane4, c64)), b, hitm);
+	const uint32_t sy = fp7<TA>(lo1, hi1, lane4, c64);
+	hitm = mad_lo(M2G == 2 ? map1g_bit(sy, gm, b) : map1_bit<TA>(sy), b, hitm);
 }
 
 /* one queued candidate (or any candidate, from the bit tile): both map levels, then park */
 template <int TA, int M2G>
 __device__ __forceinline__ void tile_candidate(const xparams *xp, uint32_t x_sa, uint32_t wa, uint32_t q, uint32_t rel,
-					       uint32_t lane4, uint32_t c64)
+					       uint32_t lane4, uint32_t c64, gmap gm)
 {
 	const uint32_t w0 = lds32o<0>(wa), x1 = lds32o<4>(wa), x2 = lds32o<8>(wa);
 	const uint32_t lo = __funnelshift_r(w0, x1, q), hi = __funnelshift_r(x1, x2, q);
 	const uint32_t sy = fp7<TA>(__funnelshift_r(lo, hi, 1), hi >> 1, lane4, c64);
-	if (map1_bit<TA>(sy) && map2_bit<TA, M2G>(sy, xp))
+	if ((M2G == 2 ? map1g_bit(sy, gm, 1u) : map1_bit<TA>(sy)) && map2_bit<TA, M2G>(sy, xp))
 		park7<TA>(xp, x_sa, rel, lo, hi);
 }
 
@@ -283,7 +299,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 		} else
 			sts32((e < 384 ? L::sa_bc + 256 * (e - 128) : L::sa_bc + 128 + 256 * (e - 384)) + 4 * l, v);
 	}
-	for (int i = threadIdx.x; i < (1 << (L::map_log2 - 2)); i += WARPS * 32) sts32(L::sa_map + 4 * i, a.map[i]);
+	if (M2G != 2)
+		for (int i = threadIdx.x; i < (1 << (L::map_log2 - 2)); i += WARPS * 32) sts32(L::sa_map + 4 * i, a.map[i]);
 	if (!M2G)
 		for (int i = threadIdx.x; i < M2_WORDS; i += WARPS * 32) sts32(L::sa_m2 + 4 * i, a.map[(1 << (L::map_log2 - 2)) + i]);
 	const uint32_t x_sa = SA_X + wid * X_BYTES;
@@ -300,6 +317,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 	__syncthreads();
 	const uint32_t lane4 = 4 * lane, my_sa = s_sa + lane4;
 	const uint32_t m1 = a.m1, c64 = a.c64;
+	const gmap gm = {a.map1g, a.m1g_shift};
 
 	for (int64_t s = s_begin; s < s_end; s++) {
 		uint32_t wv[K];
@@ -344,7 +362,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 		for (int t = 0; t < NSLOTS; t++) {
 			#pragma unroll
 			for (int k = 0; k < K; k++)
-				slot7<WIN, TA>(rem[k], hitm[k], r0[k], r1[k], r2[k], lane4, m1, c64);
+				slot7<WIN, TA, M2G>(rem[k], hitm[k], r0[k], r1[k], r2[k], lane4, m1, c64, gm);
 		}
 		/* ---- what is left: candidates beyond the inline slots (7 %) and first-level
 		 * positives (0.7 % / 1.3 %), as plain masks again ---- */
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 					while (c) {
 						const uint32_t q = bfind(c);
 						c ^= 1u << q;
-						tile_candidate<TA, M2G>(xp, x_sa, my_sa + 128 * k, q, strip_pos + (k * 32 + lane) * 32 + q, lane4, c64);
+						tile_candidate<TA, M2G>(xp, x_sa, my_sa + 128 * k, q, strip_pos + (k * 32 + lane) * 32 + q, lane4, c64, gm);
 					}
 				}
 			} else {
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 				__syncwarp();
 				for (uint32_t i = lane; i < ov; i += 32) {
 					const uint32_t e = lds16o<0>(q_sa + 2 * i);
-					tile_candidate<TA, M2G>(xp, x_sa, s_sa + (e >> 5), e, strip_pos + (e >> 7) * 32 + (e & 31), lane4, c64);
+					tile_candidate<TA, M2G>(xp, x_sa, s_sa + (e >> 5), e, strip_pos + (e >> 7) * 32 + (e & 31), lane4, c64, gm);
 				}
 				__syncwarp();
 				if (lane == 0) sts32(qn_sa, 0);

@@ -78,7 +78,7 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
 	ctx->m32 = ctx->m33 = ctx->m0 = 0;
 	ctx->d_lut6 = NULL; ctx->d_map6 = NULL;
-	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL; ctx->d_map7g = NULL;
+	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL; ctx->d_map7g = NULL; ctx->map7g_log2 = 0;
 	for (int j = 0; j < 25; j++) {
 		if (g_bit_syn[32 + j] & 1) ctx->m0 |= 1u << j;
 		if ((g_bit_syn[32 + j] >> 32) & 1) ctx->m32 |= 1u << j;
@@ -224,6 +224,7 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 			BT_CUDA_TRY(cudaMemcpy(*dst, map7.data(), map7.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		}
 		if (k == 3) {
+			ctx->map7g_log2 = 27;
 			std::vector<uint32_t> g((size_t)1 << (27 - 5), 0u);
 			auto g_add = [&](uint64_t s34) {
 				for (int c = 0; c < 2; c++) {
@@ -236,6 +237,35 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 			BT_CUDA_TRY(cudaMalloc(&ctx->d_map7g, g.size() * sizeof(uint32_t)));
 			BT_CUDA_TRY(cudaMemcpy(ctx->d_map7g, g.data(), g.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		}
+	}
+
+	/* 4 / 5 errors (982 130 / 11 060 036 reachable values): the v7 kernel's FIRST-level map in
+	 * global memory, byte = the top (log2 - 3) value bits, bit = value bits 0..2, sized for
+	 * ~1 % (k = 4: 2^27 bits, 16 MiB) and ~2 % (k = 5: 2^29 bits, 64 MiB) false positives */
+	if (k >= 4) {
+		const int lg = k == 4 ? 27 : 29;
+		ctx->map7g_log2 = lg;
+		std::vector<uint8_t> g((size_t)1 << (lg - 3), 0);
+		auto g_add = [&](uint64_t s34) {
+			for (int c = 0; c < 2; c++) {
+				uint32_t v = (uint32_t)((s34 ^ ctx->cc[c]) >> 1);
+				g[v >> (32 - (lg - 3))] |= (uint8_t)(1u << (v & 7));
+			}
+		};
+		g_add(0);
+		for (auto &e : ents) g_add(e.syn);
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_map7g, g.size()));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_map7g, g.data(), g.size(), cudaMemcpyHostToDevice));
+		std::vector<uint32_t> l7;
+		const int fw7[3] = {7, 8, 8};
+		for (int f = 0, pos = 0; f < 3; pos += fw7[f], f++)
+			for (uint32_t v = 0; v < (1u << fw7[f]); v++) {
+				uint64_t sy = 0;
+				for (int j = 0; j < fw7[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + pos + j];
+				l7.push_back((uint32_t)(sy >> 1));
+			}
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_lut7, l7.size() * sizeof(uint32_t)));
+		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut7, l7.data(), l7.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 	}
 
 	/* --- open-addressing map --- */
