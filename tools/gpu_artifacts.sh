@@ -11,4 +11,4 @@ ncu -i $O/scan_v7_full.ncu-rep --page source --csv > $O/scan_v7_full_src.csv 2>/
 rm -f $O/scan_v7_full.ncu-rep
 python tools/chain_bench.py > $O/chain_config3.json 2> $O/chain.err
 python tools/sweep.py > $O/sweep_config5.json 2> $O/sweep.err
-cat $O/bench_n1.json; cat $O/bench_reference_arm.json; tail -2 $O/*.err
+cat $O/bench_n1.json; cat $O/bench_reference_arm.json; tail -n 2 $O/*.err
