@@ -44,6 +44,8 @@ struct btbb_b200_ctx {
 	uint32_t *d_map7b;           /* ... with a 2^15-byte first-level map (layout<1>) */
 	uint32_t *d_map7g;           /* tables for 3 errors: 2^27-bit second-level map; 4 / 5 errors: 2^27 / 2^29-bit first-level map */
 	int map7g_log2;
+	int l2_persist_set;          /* cudaLimitPersistingL2CacheSize configured for the global first-level map */
+	size_t l2_persist_bytes;
 	btbb_b200_hit *d_slab;       /* slab ordering: (warps + 2) x BT_SLAB_CAP records */
 	uint32_t *d_slab_cnt;        /* per-slab fill counts (+ two 64-bit edge counters) */
 	unsigned long long *d_slab_base;

@@ -622,7 +622,37 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		if (k45) kern = v7::scan_promisc_v7<0, 5, 0, 2>;
 		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		if (k45) {
+			/* the global first-level map is probed once per candidate at random: keep it in the
+			 * persisting part of L2 while the stream (10^3 times its size) flows past it */
+			const size_t map_bytes = (size_t)1 << (ctx->map7g_log2 - 3);
+			if (!ctx->l2_persist_set) {
+				int max_persist = 0;
+				cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+				size_t want = map_bytes + (map_bytes >> 2);
+				if (want > (size_t)max_persist) want = (size_t)max_persist;
+				if (want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+				ctx->l2_persist_bytes = want;
+				ctx->l2_persist_set = 1;
+			}
+			if (ctx->l2_persist_bytes) {
+				cudaStreamAttrValue av;
+				memset(&av, 0, sizeof(av));
+				av.accessPolicyWindow.base_ptr = ctx->d_map7g;
+				av.accessPolicyWindow.num_bytes = map_bytes;
+				av.accessPolicyWindow.hitRatio = ctx->l2_persist_bytes >= map_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)map_bytes;
+				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+			}
+		}
 		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);
+		if (k45 && ctx->l2_persist_bytes) {
+			cudaStreamAttrValue av;
+			memset(&av, 0, sizeof(av));
+			av.accessPolicyWindow.num_bytes = 0;
+			cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+		}
 	} else if (use_v6) {
 		v6::args a;
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;

@@ -358,11 +358,60 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 				r0[k] = __funnelshift_r(wv[k], w1, 1); r1[k] = __funnelshift_r(w1, w2, 1); r2[k] = w2 >> 1;
 			}
 		}
-		#pragma unroll
-		for (int t = 0; t < NSLOTS; t++) {
+		if (M2G == 2 && WIN == 0) {
+			/* Global first-level map: a probe is an L2 round trip, so the slots run in two phases.
+			 * A: window + syndrome value of every in-place candidate, parked in a lane-private
+			 * column of the (otherwise unused) map area of shared memory.  B: per pair of rows,
+			 * all ten probes are issued back to back and only then looked at; the candidate bits
+			 * are enumerated a second time instead of being stored. */
+			static_assert(M2G != 2 || NSLOTS * K <= 20, "parking area holds 20 values per lane");
+			uint32_t c0[K];
 			#pragma unroll
-			for (int k = 0; k < K; k++)
-				slot7<WIN, TA, M2G>(rem[k], hitm[k], r0[k], r1[k], r2[k], lane4, m1, c64, gm);
+			for (int k = 0; k < K; k++) c0[k] = rem[k];
+			const uint32_t pend_a = L::sa_map + wid * 2048 + lane4, pend_b = L::sa_m2 + wid * 512 + lane4;
+			#pragma unroll
+			for (int t = 0; t < NSLOTS; t++) {
+				#pragma unroll
+				for (int k = 0; k < K; k++) {
+					const int j = t * K + k;
+					const uint32_t q = bfind(rem[k]);
+					rem[k] = mad_lo(onebit(q), m1, rem[k]);
+					const uint32_t sy = fp7<TA>(__funnelshift_r(r0[k], r1[k], q), __funnelshift_r(r1[k], r2[k], q), lane4, c64);
+					sts32(j < 16 ? pend_a + 128 * j : pend_b + 128 * (j - 16), sy);
+				}
+			}
+			#pragma unroll
+			for (int h = 0; h < K; h += 2) {
+				uint32_t sy[2][NSLOTS], bb[2][NSLOTS], v[2][NSLOTS];
+				#pragma unroll
+				for (int t = 0; t < NSLOTS; t++) {
+					#pragma unroll
+					for (int kk = 0; kk < 2; kk++) {
+						const int j = t * K + h + kk;
+						sy[kk][t] = lds32(j < 16 ? pend_a + 128 * j : pend_b + 128 * (j - 16));
+						bb[kk][t] = onebit(bfind(c0[h + kk]));
+						c0[h + kk] = mad_lo(bb[kk][t], m1, c0[h + kk]);
+						v[kk][t] = 0;
+						if (bb[kk][t])
+							asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v[kk][t]) : "l"(gm.p + (sy[kk][t] >> gm.shift)));
+					}
+				}
+				#pragma unroll
+				for (int t = 0; t < NSLOTS; t++) {
+					#pragma unroll
+					for (int kk = 0; kk < 2; kk++) {
+						const uint32_t x = (mul_lo(v[kk][t], 0x01010101u) >> (sy[kk][t] & 31)) & 1u;
+						hitm[h + kk] = mad_lo(x, bb[kk][t], hitm[h + kk]);
+					}
+				}
+			}
+		} else {
+			#pragma unroll
+			for (int t = 0; t < NSLOTS; t++) {
+				#pragma unroll
+				for (int k = 0; k < K; k++)
+					slot7<WIN, TA, M2G>(rem[k], hitm[k], r0[k], r1[k], r2[k], lane4, m1, c64, gm);
+			}
 		}
 		/* ---- what is left: candidates beyond the inline slots (7 %) and first-level
 		 * positives (0.7 % / 1.3 %), as plain masks again ---- */
