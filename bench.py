@@ -359,7 +359,7 @@ def main():
                            "symbols_per_gpu": n, "total_symbols": total_positions, "max_ac_errors": K_ERRORS,
                            "planted_stride": STRIDE, "hits_total": total_hits, "seam_symbols": sharding.SEAM,
                            "l2": "input (10 GB/GPU) is far larger than the 126 MB L2; no flush needed",
-                           "parallelism": f"contiguous shards x{world}, padded NCCL all-gather of hit records"},
+                           "parallelism": f"contiguous shards x{world}, one NCCL all-gather of fixed-size hit-record slots"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * steps,
                 "clocks": clocks}
         emit(line)

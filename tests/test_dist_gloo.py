@@ -27,6 +27,11 @@ shard = B.synth_host(B.synth_cfg(rs - rb, stride=3000, ber=0.002, mix=('ID', 'DM
 h = util.find_all(O, 'orc', shard, e - b, B.LAP_ANY, 2)
 h['offset'] += b
 local = torch.from_numpy(h.view(np.uint8).reshape(-1, 16).copy())
+# a first, small exchange fixes the slot size; the real one then outgrows it on both ranks and
+# has to re-agree (sharding.gather_hits)
+few, few_counts = sharding.gather_hits(local[: 3 + rank])
+assert few_counts == [3, 4] and few.shape[0] == 7
+assert torch.equal(few[3:], local.new_tensor(few[3:]))
 allh, counts = sharding.gather_hits(local)
 if rank == 0:
     whole = B.synth_host(cfg)
