@@ -72,7 +72,6 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_tmp2) cudaFree(ctx->d_tmp2);
 	if (ctx->d_sort_hist) cudaFree(ctx->d_sort_hist);
 	if (ctx->d_xp) cudaFree(ctx->d_xp);
-	if (ctx->d_dbg) cudaFree(ctx->d_dbg);
 	if (ctx->d_unpack) cudaFree(ctx->d_unpack);
 	if (ctx->d_packed) cudaFree(ctx->d_packed);
 	if (ctx->d_sieve_tc) cudaFree(ctx->d_sieve_tc);

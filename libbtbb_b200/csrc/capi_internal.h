@@ -35,10 +35,6 @@ struct btbb_b200_ctx {
 	uint64_t cc[2];              /* 34-bit syndrome of PN ^ (legal tail << 57) */
 	uint32_t m32, m33;           /* parity masks over codeword bits 32..56 for syndrome bits 32 / 33 */
 	uint32_t m0;                 /* same for syndrome bit 0 */
-	uint32_t *d_dbg;             /* developer counters (BTBB_B200_DBG=1) */
-	int dbg_n;
-	uint32_t *d_lut6;            /* bulk kernel v6: byte tables over codeword bits 41..48 / 49..56 / 33..40 -> syndrome bits 1..32 */
-	uint32_t *d_map6;            /* bulk kernel v6: 2^19-bit + 2^17-bit maps over syndrome bits 1..32 */
 	uint32_t *d_lut7;            /* bulk kernel v7: field tables over codeword bits 34..40 / 41..48 / 49..56 -> syndrome bits 1..32 */
 	uint32_t *d_map7;            /* bulk kernel v7: 2^16-byte first-level map + 2^17-bit second-level map */
 	uint32_t *d_map7b;           /* ... with a 2^15-byte first-level map (layout<1>) */

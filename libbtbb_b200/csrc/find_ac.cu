@@ -388,7 +388,6 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 
 #include "scan_v3.cuh"
 #include "scan_v4.cuh"
-#include "scan_v6.cuh"
 #include "scan_v7.cuh"
 #include "scan_known.cuh"
 
@@ -514,16 +513,13 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	}
 	if (packed) env = NULL;      /* the developer switches below are for the byte format */
 	/* promiscuous default: scan_v7.cuh for the byte format, scan_v4.cuh (LUTMODE 2, five in-place
-	 * slots) for packed input.  BTBB_B200_SCAN=v6.. selects the experimental scan_v6.cuh, whose
-	 * windows start one symbol before the aligned data it loads (so it wants at least one symbol
-	 * in front); v3 / v4a.. the older generations, v7 / v7f / .. the v7 variants */
-	const bool use_v6 = !known && !packed && !k3 && env && !strncmp(env, "v6", 2);
+	 * slots) for packed input.  BTBB_B200_SCAN=v3 / v4a.. select the older generations,
+	 * v7 / v7f / .. the v7 variants (developer A/B runs, tools/kbench.py) */
 	/* byte-format promiscuous scans run scan_v7.cuh unless an older generation is asked for */
-	const bool use_v7 = k3 || (!known && !packed && !use_v6 && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3"))));
+	const bool use_v7 = k3 || (!known && !packed && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3"))));
 	const char *env7 = env && !strncmp(env, "v7", 2) ? env : NULL;
 	int64_t al = packed ? 0 : (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
-	if (use_v6 && al == 0) al = 32;
-	const int64_t head = use_v6 ? al - 1 : al;                                             /* first window of the bulk kernel */
+	const int64_t head = al;                                                               /* first window of the bulk kernel */
 	/* a strip reads 64 symbols past its end and the stream holds n + 63 */
 	int64_t nstrips = n - 1 > al ? (n - 1 - al) / v3::STRIP : 0;
 	/* the bulk kernels carry 32-bit positions relative to a warp's run: keep a launch below
@@ -543,12 +539,10 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	v3::xparams xp;
 	memset(&xp, 0, sizeof(xp));
 	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
-	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0; xp.stream = packed ? NULL : d_stream;
+	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0;
 	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err; xp.map2g = ctx->d_map7g;
 	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
-	int bulk_warps = 32;
-	if (use_v6 && env && !strncmp(env, "v6w24", 5)) bulk_warps = 24;
-	else if (use_v6 && env && !strncmp(env, "v6w16", 5)) bulk_warps = 16;
+	const int bulk_warps = 32;
 	int64_t grid = ctx->sm_count;
 	const int64_t need = (nstrips + bulk_warps - 1) / bulk_warps;
 	if (grid > need) grid = need;
@@ -560,10 +554,6 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_slab_cnt, 0, (size_t)(nw + 2) * sizeof(uint32_t) + 2 * sizeof(unsigned long long), st));
 		xp.slab = ctx->d_slab; xp.slab_cnt = ctx->d_slab_cnt; xp.slab_cap = BT_SLAB_CAP;
 		slab->used = 1; slab->nw = nw;
-	}
-	if (getenv("BTBB_B200_DBG")) {
-		if (!ctx->d_dbg) BT_CUDA_TRY(cudaMalloc(&ctx->d_dbg, 148 * 32 * 32));
-		xp.dbg = ctx->d_dbg; ctx->dbg_n = (int)grid * bulk_warps;
 	}
 	if (!ctx->d_xp)
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_xp, 16 * 128));
@@ -653,18 +643,6 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 			av.accessPolicyWindow.num_bytes = 0;
 			cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
 		}
-	} else if (use_v6) {
-		v6::args a;
-		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
-		a.lut = ctx->d_lut6; a.map = ctx->d_map6; a.xp = (const v3::xparams *)slot;
-		void (*kern)(const v6::args) = v6::scan_promisc_v6<5, 32>;
-		if (env && !strcmp(env, "v6s4")) kern = v6::scan_promisc_v6<4, 32>;
-		else if (env && !strcmp(env, "v6s6")) kern = v6::scan_promisc_v6<6, 32>;
-		else if (env && !strcmp(env, "v6w24")) kern = v6::scan_promisc_v6<5, 24>;
-		else if (env && !strcmp(env, "v6w16")) kern = v6::scan_promisc_v6<5, 16>;
-		else if (env && !strcmp(env, "v6w24s4")) kern = v6::scan_promisc_v6<4, 24>;
-		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v6::SMEM_BYTES));
-		kern<<<(unsigned)grid, bulk_warps * 32, v6::SMEM_BYTES, st>>>(a);
 	} else if (env && !strcmp(env, "v3")) {
 		v3::args a;
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
@@ -992,11 +970,3 @@ int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed,
 	return BTBB_B200_OK;
 }
 
-/* developer: copy the per-warp counters of the last bulk launch (BTBB_B200_DBG=1) */
-extern "C" int bt_dbg_read(btbb_b200_ctx *ctx, uint32_t *out, int max_warps)
-{
-	if (!ctx || !ctx->d_dbg) return 0;
-	int n = ctx->dbg_n < max_warps ? ctx->dbg_n : max_warps;
-	if (cudaMemcpy(out, ctx->d_dbg, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-	return n;
-}

@@ -76,9 +76,7 @@ struct xparams {
 	btbb_b200_hit *slab;
 	uint32_t *slab_cnt;
 	uint32_t slab_cap;
-	uint32_t m0;             /* like m32: codeword bits 32..56 feeding syndrome bit 0 (scan_v6.cuh) */
-	const uint8_t *stream;   /* stream[pos] = symbol at launch-relative position pos (scan_v6.cuh) */
-	uint32_t *dbg;           /* developer: per-warp {leftover-loop trips, cycles} (BTBB_B200_DBG=1), else NULL */
+	uint32_t m0;             /* like m32: codeword bits 32..56 feeding syndrome bit 0 (scan_v7.cuh) */
 	const uint32_t *map2g;   /* scan_v7.cuh with tables for 3 errors: 2^27-bit second-level map in global memory */
 };
 

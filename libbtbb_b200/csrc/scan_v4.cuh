@@ -315,7 +315,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 	}
 	__syncthreads();
 	const uint32_t lane4 = 4 * lane, my_sa = s_sa + lane4;
-	const long long dbg_t0 = clock64();
 
 	for (int64_t s = s_begin; s < s_end; s++) {
 		uint32_t wv[K];
@@ -419,10 +418,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v4(const args a)
 		if (lds32(x_sa) >= XCAP / 2) flush4<LUTMODE>(xp, x_sa, lane);
 	}
 	flush4<LUTMODE>(xp, x_sa, lane);
-	if (xp->dbg && lane == 0) {
-		for (int j = 0; j < 8; j++) xp->dbg[8 * gw + j] = 0;
-		xp->dbg[8 * gw + 2] = (uint32_t)(clock64() - dbg_t0); xp->dbg[8 * gw + 3] = (uint32_t)(s_end - s_begin);
-	}
 }
 
 }  // namespace v4

@@ -10,8 +10,8 @@
  *
  *   enumerate  the candidate mask is kept bit-reversed; lowest set bit b = c & -c, where -c and
  *              c - b are IMADs.  b = 2^(31-q) for the candidate at bit q;
- *   window     (W * b) >> 32 = W >> (q + 1): the filter works on syndrome bits 1..32 (as
- *              scan_v6.cuh does), whose identity part is window bits 1..32, so the two words it
+ *   window     (W * b) >> 32 = W >> (q + 1): the filter works on syndrome bits 1..32, whose
+ *              identity part is window bits 1..32, so the two words it
  *              needs -- window bits 1..32 and 33..64 -- are two IMAD.HI + two IMAD on the
  *              lane's three stream words as they are (WIN = 1), instead of FLO + BMSK + two
  *              funnel shifts (WIN = 0, kept for A/B runs);

@@ -77,7 +77,6 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	ctx->cc[0] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_A << 57));
 	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
 	ctx->m32 = ctx->m33 = ctx->m0 = 0;
-	ctx->d_lut6 = NULL; ctx->d_map6 = NULL;
 	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL; ctx->d_map7g = NULL; ctx->map7g_log2 = 0;
 	for (int j = 0; j < 25; j++) {
 		if (g_bit_syn[32 + j] & 1) ctx->m0 |= 1u << j;
@@ -156,37 +155,9 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut2, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_map2, map.size() * sizeof(uint32_t)));
 		BT_CUDA_TRY(cudaMemcpy(ctx->d_map2, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		/* v6 works on syndrome bits 1..32 (its windows are addressed one symbol late, see
-		 * scan_v6.cuh): byte tables A / B / C over codeword bits 41..48 / 49..56 / 33..40 (bit 33
-		 * only reaches syndrome bit 33, so C ignores its index bit 0), and the same two maps
-		 * over that 32-bit value */
-		{
-			std::vector<uint32_t> l6;
-			const int first[3] = {41, 49, 33};
-			for (int f = 0; f < 3; f++)
-				for (uint32_t v = 0; v < 256; v++) {
-					uint64_t sy = 0;
-					for (int j = 0; j < 8; j++) if ((v >> j) & 1) sy ^= g_bit_syn[first[f] + j];
-					l6.push_back((uint32_t)(sy >> 1));
-				}
-			BT_CUDA_TRY(cudaMalloc(&ctx->d_lut6, l6.size() * sizeof(uint32_t)));
-			BT_CUDA_TRY(cudaMemcpy(ctx->d_lut6, l6.data(), l6.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-			std::vector<uint32_t> map6(m1_words + m2_words, 0u);
-			auto map6_add = [&](uint64_t s34) {
-				for (int c = 0; c < 2; c++) {
-					uint32_t v = (uint32_t)((s34 ^ ctx->cc[c]) >> 1);
-					map6[v >> 18] |= 1u << (v & 31);
-					map6[m1_words + ((v >> 10) & (m2_words - 1))] |= 1u << ((v >> 5) & 31);
-				}
-			};
-			map6_add(0);
-			for (auto &e : ents) map6_add(e.syn);
-			BT_CUDA_TRY(cudaMalloc(&ctx->d_map6, map6.size() * sizeof(uint32_t)));
-			BT_CUDA_TRY(cudaMemcpy(ctx->d_map6, map6.data(), map6.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		}
 	}
 
-	/* v7 (scan_v7.cuh) works on syndrome bits 1..32 like v6: field tables A / B / C over
+	/* v7 (scan_v7.cuh) works on syndrome bits 1..32: field tables A / B / C over
 	 * codeword bits 34..40 / 41..48 / 49..56, a first-level map addressed by byte (byte = the
 	 * top 16 / 15 value bits, bit = bits 0..2) and a second-level map -- for k <= 2 in shared
 	 * memory over value bits 3..19 (word = bits 8..19, bit = bits 3..7), for k = 3 (68 558
@@ -297,14 +268,12 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_lut4) cudaFree(ctx->d_lut4);
 	if (ctx->d_lut2b) cudaFree(ctx->d_lut2b);
 	if (ctx->d_lut3) cudaFree(ctx->d_lut3);
-	if (ctx->d_lut6) cudaFree(ctx->d_lut6);
-	if (ctx->d_map6) cudaFree(ctx->d_map6);
 	if (ctx->d_lut7) cudaFree(ctx->d_lut7);
 	if (ctx->d_map7) cudaFree(ctx->d_map7);
 	if (ctx->d_map7b) cudaFree(ctx->d_map7b);
 	if (ctx->d_map7g) cudaFree(ctx->d_map7g);
 	ctx->d_map7g = NULL;
-	ctx->d_lut6 = NULL; ctx->d_map6 = NULL; ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL;
+	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL;
 	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
 	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL; ctx->d_lut2b = NULL; ctx->d_lut3 = NULL;
 }
