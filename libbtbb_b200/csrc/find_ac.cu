@@ -503,7 +503,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	/* tables for 3 errors: only the byte-format v7 kernel has a bulk path (global second-level map) */
 	const bool k3 = !known && !ctx->d_map2 && ctx->d_map7g;      /* 3, 4 or 5 */
 	const bool k45 = k3 && ctx->table_k >= 4;
-	if ((!known && !ctx->d_map2 && !(k3 && !packed)) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
+	if ((!known && !ctx->d_map2 && !k3) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
 		if (packed) {      /* no bulk kernel for this case: expand to the byte format and take the tile kernel */
 			int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), 0, n + 63, st);
 			if (rc0) return rc0;
@@ -512,11 +512,10 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	}
 	if (packed) env = NULL;      /* the developer switches below are for the byte format */
-	/* promiscuous default: scan_v7.cuh for the byte format, scan_v4.cuh (LUTMODE 2, five in-place
-	 * slots) for packed input.  BTBB_B200_SCAN=v3 / v4a.. select the older generations,
+	/* promiscuous default: scan_v7.cuh.  BTBB_B200_SCAN=v3 / v4a.. select the older generations,
 	 * v7 / v7f / .. the v7 variants (developer A/B runs, tools/kbench.py) */
 	/* byte-format promiscuous scans run scan_v7.cuh unless an older generation is asked for */
-	const bool use_v7 = k3 || (!known && !packed && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3"))));
+	const bool use_v7 = k3 || (!known && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3"))));
 	const char *env7 = env && !strncmp(env, "v7", 2) ? env : NULL;
 	int64_t al = packed ? 0 : (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
 	const int64_t head = al;                                                               /* first window of the bulk kernel */
@@ -610,6 +609,8 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		if (k3) kern = env7 && !strcmp(env7, "v7fs6") ? v7::scan_promisc_v7<0, 6, 0, 1> : v7::scan_promisc_v7<0, 5, 0, 1>;
 		/* 4 / 5-error tables: first level in global memory, positives straight to the exact test */
 		if (k45) kern = v7::scan_promisc_v7<0, 5, 0, 2>;
+		if (packed) kern = k45 ? v7::scan_promisc_v7<0, 5, 0, 2, true> : k3 ? v7::scan_promisc_v7<0, 5, 0, 1, true>
+				       : v7::scan_promisc_v7<0, 5, 1, 0, true>;
 		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		if (k45) {

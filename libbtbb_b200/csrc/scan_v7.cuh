@@ -277,7 +277,10 @@ __device__ __forceinline__ void tile_candidate(const xparams *xp, uint32_t x_sa,
 		park7<TA>(xp, x_sa, rel, lo, hi);
 }
 
-template <int WIN, int NSLOTS, int TA, int M2G = 0>
+/* PACKED: a.base points at the stream already packed 32 symbols per word, LSB first (format B of
+ * SURVEY.md 8d; the host entry points pack before the PCIe copy): the load / pack stage becomes
+ * one 4-byte load per lane and row */
+template <int WIN, int NSLOTS, int TA, int M2G = 0, bool PACKED = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 {
 	typedef layout<TA> L;
@@ -322,7 +325,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 	for (int64_t s = s_begin; s < s_end; s++) {
 		uint32_t wv[K];
 		/* ---- load + pack ---- */
-		{
+		if (PACKED) {
+			const uint32_t *pw = reinterpret_cast<const uint32_t *>(a.base) + s * SW + lane;
+			#pragma unroll
+			for (int k = 0; k < K; k++) wv[k] = v3::ldg32(pw + 32 * k);
+			uint32_t halo = 0;
+			if (lane < 2) halo = v3::ldg32(pw + SW);                /* words 0 / 1 of the next strip */
+			if (s + 1 < s_end && lane < K)
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(pw - lane + SW + 32 * lane));
+			#pragma unroll
+			for (int k = 0; k < K; k++) sts32(my_sa + 128 * k, wv[k]);
+			if (lane < 2) sts32(my_sa + 128 * K, halo);
+		} else {
 			uint32_t raw[K][8];
 			const uint8_t *p = a.base + s * STRIP + lane * 32;
 			#pragma unroll

@@ -224,6 +224,38 @@ def test_packed_ingest_matches_oracle(gpu_ctx2, orc, n):
         assert got == want.tobytes(), (n, hex(lap), k)
 
 
+@pytest.mark.parametrize("k_init", [3, 4])
+def test_packed_and_byte_ingest_with_larger_tables(product_lib, k_init):
+    """Tables for 3 / 4 errors take the bulk kernel's global-memory map variants, for both input
+    formats; outputs recorded from the reference in a subprocess-free way: the oracle with the
+    same table size."""
+    import subprocess, sys, torch
+    n = 300_001
+    rng = np.random.default_rng(500 + k_init)
+    s = rng.integers(0, 2, n + 63, dtype=np.uint8)
+    util.plant_syncwords(s, rng, 60, k_init)
+    # the oracle's table is built once per process (like the reference's): ask a fresh interpreter
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import util; from util import B; "
+            "O = util.oracle(); assert O.orc_init(%d) == 0; s = np.load(sys.argv[1]); "
+            "h = util.find_all(O, 'orc', s, %d, B.LAP_ANY, %d); np.save(sys.argv[2], h)") % (
+                util.ROOT, os.path.join(util.ROOT, "tests"), k_init, n, k_init)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        np.save(os.path.join(td, "s.npy"), s)
+        subprocess.run([sys.executable, "-c", code, os.path.join(td, "s.npy"), os.path.join(td, "h.npy")], check=True)
+        want = np.load(os.path.join(td, "h.npy"))
+    assert len(want) >= 40          # (errors planted in the Barker tail can put a sync word out of reach)
+    d_words = torch.from_numpy(_pack_words(s).view(np.int32)).cuda()
+    d_bytes = torch.from_numpy(s).cuda()
+    cap = 1 << 16
+    d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    with B.Context(0, k_init) as ctx:
+        cnt, rc = ctx.find_ac_packed_dev(d_words.data_ptr(), n, d_hits.data_ptr(), cap, k=k_init)
+        assert rc == 0 and d_hits[:cnt].cpu().numpy().tobytes() == want.tobytes(), ("packed", cnt, len(want))
+        cnt, rc = ctx.find_ac_dev(d_bytes.data_ptr(), n, d_hits.data_ptr(), cap, k=k_init)
+        assert rc == 0 and d_hits[:cnt].cpu().numpy().tobytes() == want.tobytes(), ("bytes", cnt, len(want))
+
+
 def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc, monkeypatch):
     """>= 4 Mi symbols: find_ac_host packs on the host before the copy; the byte-format copy
     (BTBB_B200_HOST=bytes) and the oracle must give the same records, pageable memory included."""
