@@ -233,23 +233,69 @@ def main():
     d_count = torch.zeros(2, dtype=torch.int64, device="cuda")
     ctx = B.Context(local, K_ERRORS)
 
+    # hit buffers alternate between steps: the exchange of step i is still in flight (copy engines)
+    # while step i + 1 scans
+    d_hits2 = torch.zeros_like(d_hits) if world > 1 else None
+    peer = None
+    if world > 1 and os.environ.get("BTBB_B200_GATHER", "peer") == "peer":
+        try:
+            peer = sharding.PeerGather(cap, torch.device("cuda", local))
+        except Exception as ex:                     # no symmetric memory on this box / build: NCCL gather
+            sys.stderr.write(f"[bench] peer-memory gather unavailable ({ex!r}); using the NCCL all-gather\n")
+            peer = None
+    flip = [0]
+    if world > 1:
+        ctx.set_offset_bias(begin)                     # the kernels report global offsets
+
     def step():
-        cnt, rc = ctx.find_ac_dev(d_stream.data_ptr(), n, d_hits.data_ptr(), cap, lap=B.LAP_ANY, k=K_ERRORS, stream=st)
+        buf = d_hits if (world == 1 or flip[0] == 0) else d_hits2
+        flip[0] ^= 1
+        cnt, rc = ctx.find_ac_dev(d_stream.data_ptr(), n, buf.data_ptr(), cap, lap=B.LAP_ANY, k=K_ERRORS, stream=st)
         assert rc == 0
         if world > 1:
-            mine = d_hits[:cnt]
-            mine.view(torch.int64)[:, 0] += begin          # global offsets (the buffer is rewritten every step)
-            _, counts = sharding.gather_hits(mine, concat=False)
+            _, counts = sharding.gather_hits(buf[:cnt], concat=False)
             return cnt, int(sum(counts))
         return cnt, cnt
+
+    def run_steps(k):
+        """k whole steps.  With the peer-memory exchange the steps are pipelined: the scan of step
+        i + 1 is enqueued before the exchange of step i, whose copies then run on the copy engines
+        underneath it; the last exchange is complete when this returns."""
+        if peer is None:
+            for _ in range(k):
+                local_hits, total_hits = step()
+            return local_hits, total_hits
+        bufs = (d_hits, d_hits2)
+        # PeerGather's generations alternate like the hit buffers: generation == buffer index
+        assert peer.gen == flip[0]
+        peer.wait_sent(flip[0])
+        ctx.find_ac_dev_begin(d_stream.data_ptr(), n, bufs[flip[0]].data_ptr(), cap, lap=B.LAP_ANY, k=K_ERRORS, stream=st)
+        for i in range(k):
+            cur = bufs[flip[0]]
+            flip[0] ^= 1
+            cnt, rc = ctx.find_ac_dev_end()
+            assert rc == 0
+            if i + 1 < k:
+                peer.wait_sent(flip[0])
+                ctx.find_ac_dev_begin(d_stream.data_ptr(), n, bufs[flip[0]].data_ptr(), cap, lap=B.LAP_ANY, k=K_ERRORS, stream=st)
+            peer.start(cur[:cnt])
+        _, counts = peer.finish()
+        return cnt, int(sum(counts))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        local_hits, total_hits = step()
+    local_hits, total_hits = run_steps(warmup)
+    if peer is not None:
+        # the peer-memory exchange must deliver exactly what the NCCL all-gather does
+        buf = d_hits2 if flip[0] == 0 else d_hits
+        slots, counts = peer.finish()
+        ref_slots, ref_counts = sharding.gather_hits(buf[:local_hits], concat=False)
+        assert counts == ref_counts, (counts, ref_counts)
+        for r, c in enumerate(counts):
+            assert torch.equal(slots[r, :c], ref_slots[r, :c]), f"peer gather differs from NCCL in slot {r}"
     # ---- timed region: K whole steps, device clock, max over ranks ----
     sampler = ClockSampler(local)
     barrier()
@@ -258,8 +304,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(steps):
-        local_hits, total_hits = step()
+    local_hits, total_hits = run_steps(steps)
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -359,7 +404,7 @@ def main():
                            "symbols_per_gpu": n, "total_symbols": total_positions, "max_ac_errors": K_ERRORS,
                            "planted_stride": STRIDE, "hits_total": total_hits, "seam_symbols": sharding.SEAM,
                            "l2": "input (10 GB/GPU) is far larger than the 126 MB L2; no flush needed",
-                           "parallelism": f"contiguous shards x{world}, one NCCL all-gather of fixed-size hit-record slots"},
+                           "parallelism": f"contiguous shards x{world}, " + ("all-gather of hit records over NVLink peer memory (copy engines, overlapped with the next scan)" if peer is not None else "one NCCL all-gather of fixed-size hit-record slots")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * steps,
                 "clocks": clocks}
         emit(line)

@@ -106,6 +106,23 @@ int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t s
 			  void *cuda_stream);
 
 /*
+ * btbb_b200_find_ac_dev in two halves, for callers that pipeline: _begin enqueues the scan and
+ * the ordering pass on cuda_stream and returns without waiting; _end waits for them and
+ * delivers the count and the status (in the uncommon cases -- known-LAP scans, very dense
+ * hits -- it still has work to enqueue and wait for).  One call can be pending per context;
+ * d_hits must stay untouched in between.  btbb_b200_find_ac_dev is _begin followed by _end.
+ */
+int btbb_b200_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+				uint32_t lap, int max_ac_errors,
+				btbb_b200_hit *d_hits, int64_t max_hits, void *cuda_stream);
+int btbb_b200_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits);
+
+/* Added to every offset btbb_b200_find_ac_dev / _packed_dev / _dev_begin report from now on (0
+ * after btbb_b200_create): a rank that scans one shard of a longer stream gets global offsets
+ * straight from the kernels. */
+int btbb_b200_set_offset_bias(btbb_b200_ctx *ctx, int64_t bias);
+
+/*
  * btbb_b200_find_ac_dev for a stream that is already PACKED, 32 symbols per word: symbol i of
  * the stream is bit (i & 31) of d_words[i >> 5] -- the reference's own bit order when it packs
  * a window (air_to_host64, bluetooth_packet.c:235-242: symbol i <-> bit i).  This is the

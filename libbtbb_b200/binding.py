@@ -66,6 +66,9 @@ _PROTOS = {
     "btbb_b200_table_errors": (_int, [_vp]),
     "btbb_b200_last_error": (C.c_char_p, []),
     "btbb_b200_find_ac_dev": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64), _vp]),
+    "btbb_b200_find_ac_dev_begin": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, _vp]),
+    "btbb_b200_find_ac_dev_end": (_int, [_vp, C.POINTER(_i64)]),
+    "btbb_b200_set_offset_bias": (_int, [_vp, _i64]),
     "btbb_b200_find_ac_packed_dev": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64), _vp]),
     "btbb_b200_find_ac_enqueue": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, _vp, _vp]),
     "btbb_b200_find_ac_host": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64)]),
@@ -176,6 +179,18 @@ class Context:
         n = _i64(0)
         rc = lib().btbb_b200_find_ac_dev(self.h, d_ptr, search_length, lap, k, d_hits_ptr, max_hits,
                                          C.byref(n), stream)
+        check(rc, allow=(-4,))
+        return n.value, rc
+
+    def set_offset_bias(self, bias):
+        check(lib().btbb_b200_set_offset_bias(self.h, bias))
+
+    def find_ac_dev_begin(self, d_ptr, search_length, d_hits_ptr, max_hits, lap=LAP_ANY, k=2, stream=0):
+        check(lib().btbb_b200_find_ac_dev_begin(self.h, d_ptr, search_length, lap, k, d_hits_ptr, max_hits, stream))
+
+    def find_ac_dev_end(self):
+        n = _i64(0)
+        rc = lib().btbb_b200_find_ac_dev_end(self.h, C.byref(n))
         check(rc, allow=(-4,))
         return n.value, rc
 

@@ -76,6 +76,7 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_packed) cudaFree(ctx->d_packed);
 	if (ctx->d_sieve_tc) cudaFree(ctx->d_sieve_tc);
 	if (ctx->d_sieve_present) cudaFree(ctx->d_sieve_present);
+	if (ctx->h_res) cudaFreeHost(ctx->h_res);
 	if (ctx->d_sieve_idx) cudaFree(ctx->d_sieve_idx);
 	if (ctx->d_sieve_cur) cudaFree(ctx->d_sieve_cur);
 	for (int i = 0; i < 2; i++) if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
@@ -277,10 +278,6 @@ static int pack_and_upload(btbb_b200_ctx *ctx, const char *stream, int64_t nsym)
 			BT_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking));
 	if (total_words + 2 > ctx->packed_cap) {
 		if (ctx->d_packed) cudaFree(ctx->d_packed);
-	if (ctx->d_sieve_tc) cudaFree(ctx->d_sieve_tc);
-	if (ctx->d_sieve_present) cudaFree(ctx->d_sieve_present);
-	if (ctx->d_sieve_idx) cudaFree(ctx->d_sieve_idx);
-	if (ctx->d_sieve_cur) cudaFree(ctx->d_sieve_cur);
 		ctx->d_packed = NULL; ctx->packed_cap = 0;
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_packed, (size_t)(total_words + 2) * sizeof(uint32_t)));
 		ctx->packed_cap = total_words + 2;

@@ -20,6 +20,18 @@ struct bt_scan_tables {
  * bluetooth_packet.c:121-145).  Empty slots have syn == 0 (no error pattern has a zero syndrome). */
 struct bt_err_slot { uint64_t syn, err; };
 
+/* one find_ac call between its begin() and end() halves (find_ac.cu) */
+enum { BT_PENDING_NONE = 0, BT_PENDING_EMPTY, BT_PENDING_SLAB, BT_PENDING_UNORDERED, BT_PENDING_GENERIC };
+struct bt_pending {
+	int mode;
+	const uint8_t *d_stream;
+	int packed, max_ac_errors;
+	int64_t search_length, max_hits;
+	uint32_t lap;
+	btbb_b200_hit *d_hits;
+	cudaStream_t st;
+};
+
 struct btbb_b200_ctx {
 	int device;
 	int table_k;                 /* tables hold every pattern of 1..table_k errors in bits 0..57 */
@@ -68,6 +80,9 @@ struct btbb_b200_ctx {
 	int64_t h_pack_cap;          /* words each */
 	int64_t stage_cap;
 	cudaStream_t copy_stream[2];
+	bt_pending pending;
+	int64_t hit_bias;            /* added to every offset the device entry points report (btbb_b200_set_offset_bias) */
+	unsigned long long *h_res;   /* pinned: {hit count, slab-overflow flag} of the pending call */
 	uint16_t *d_sieve_tc;        /* UAP sieve: (packet, clock) table, 64 words per packet */
 	uint8_t *d_sieve_present;    /* UAP sieve: btbb_header_present per packet */
 	int64_t sieve_cap;           /* packets the two buffers hold */
@@ -92,6 +107,9 @@ int bt_ensure_slab(btbb_b200_ctx *ctx, int nslabs);
 int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		      btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
 		      int64_t bias, cudaStream_t st, bt_slab_req *slab, int packed = 0);
+int bt_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			 int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, cudaStream_t st);
+int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits);
 int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
 			int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits, cudaStream_t st);
 int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits);

@@ -894,48 +894,83 @@ extern "C" int btbb_b200_find_ac_packed_dev(btbb_b200_ctx *ctx, const uint32_t *
 				   d_hits, max_hits, n_hits, (cudaStream_t)cuda_stream);
 }
 
-/* device-resident stream (bytes, or packed words when `packed`) -> ascending hit list in d_hits */
-int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
-			int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits, cudaStream_t st)
+/* device-resident stream (bytes, or packed words when `packed`) -> ascending hit list in d_hits.
+ * Split in two so that a caller can overlap its own host work (or the next call's set-up) with
+ * the kernels: begin() enqueues everything the common case needs -- scan, slab scan, slab sort,
+ * the read-back of the counters into pinned memory -- and returns; end() waits, and only in the
+ * uncommon cases (no slab ordering for this call, or a slab overflowed) runs the generic path. */
+int bt_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			 int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, cudaStream_t st)
 {
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
-	*n_hits = 0;
-	if (search_length == 0) return BTBB_B200_OK;
+	bt_pending &pd = ctx->pending;
+	if (pd.mode != BT_PENDING_NONE)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: a call is already pending on this context");
+	pd.d_stream = d_stream; pd.packed = packed; pd.search_length = search_length; pd.lap = lap;
+	pd.max_ac_errors = max_ac_errors; pd.d_hits = d_hits; pd.max_hits = max_hits; pd.st = st;
+	pd.mode = BT_PENDING_GENERIC;
+	if (search_length == 0) { pd.mode = BT_PENDING_EMPTY; return BTBB_B200_OK; }
 	int rc = bt_ensure_tmp(ctx, max_hits > 0 ? max_hits : 1);
-	if (rc) return rc;
-	unsigned long long total = 0;
+	if (rc) { pd.mode = BT_PENDING_NONE; return rc; }
+	if (!ctx->h_res) {
+		cudaError_t e = cudaMallocHost(&ctx->h_res, 2 * sizeof(unsigned long long));
+		if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "cudaMallocHost(find_ac counters)"); }
+	}
+	if (lap != BTBB_B200_LAP_ANY) return BTBB_B200_OK;       /* known LAP: the generic path, in end() */
 	/* fast ordering: per-warp slabs, one small sort per slab (promiscuous bulk path only) */
-	if (lap == BTBB_B200_LAP_ANY) {
-		bt_slab_req req;
-		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(unsigned long long), st));
-		rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, 0, st, &req, packed);
-		if (rc) return rc;
-		if (req.used) {
-			const int nw = req.nw;
-			unsigned long long *edge_cnt = (unsigned long long *)(ctx->d_slab_cnt + ((nw + 2 + 1) & ~1));
-			slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count);
-			unsigned long long res2[2] = {0, 0};
-			BT_CUDA_TRY(cudaMemcpyAsync(res2, ctx->d_count, sizeof(res2), cudaMemcpyDeviceToHost, st));
-			BT_CUDA_TRY(cudaStreamSynchronize(st));
-			if (res2[0] >> 62)
-				return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
-			if (!res2[1]) {
-				total = res2[0];
+	bt_slab_req req;
+	cudaError_t e = cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(unsigned long long), st);
+	if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "cudaMemsetAsync(find_ac counters)"); }
+	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, ctx->hit_bias, st, &req, packed);
+	if (rc) { pd.mode = BT_PENDING_NONE; return rc; }
+	if (req.used) {
+		const int nw = req.nw;
+		unsigned long long *edge_cnt = (unsigned long long *)(ctx->d_slab_cnt + ((nw + 2 + 1) & ~1));
+		slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count);
+		/* the sort is safe to run even if a slab overflowed (counts are clamped); its output is
+		 * then simply not used */
+		slab_sort_kernel<<<nw + 2, 256, 0, st>>>(ctx->d_slab, ctx->d_slab_cnt, ctx->d_slab_base, d_hits, max_hits);
+		pd.mode = BT_PENDING_SLAB;
+	} else
+		pd.mode = BT_PENDING_UNORDERED;      /* the unordered list is in d_tmp, its length in d_count[0] */
+	e = cudaMemcpyAsync(ctx->h_res, ctx->d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaGetLastError();
+	if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "find_ac: enqueue"); }
+	return BTBB_B200_OK;
+}
+
+int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
+{
+	bt_pending pd = ctx->pending;
+	ctx->pending.mode = BT_PENDING_NONE;
+	*n_hits = 0;
+	if (pd.mode == BT_PENDING_NONE)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: no call is pending on this context");
+	if (pd.mode == BT_PENDING_EMPTY) return BTBB_B200_OK;
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	cudaStream_t st = pd.st;
+	const uint8_t *d_stream = pd.d_stream;
+	const int packed = pd.packed, max_ac_errors = pd.max_ac_errors;
+	const int64_t search_length = pd.search_length, max_hits = pd.max_hits;
+	const uint32_t lap = pd.lap;
+	btbb_b200_hit *d_hits = pd.d_hits;
+	unsigned long long total = 0;
+	int rc;
+	if (pd.mode == BT_PENDING_SLAB || pd.mode == BT_PENDING_UNORDERED) {
+		BT_CUDA_TRY(cudaStreamSynchronize(st));
+		if (ctx->h_res[0] >> 62)
+			return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
+		if (pd.mode == BT_PENDING_SLAB) {
+			if (!ctx->h_res[1]) {
+				total = ctx->h_res[0];
 				*n_hits = (int64_t)total;
-				slab_sort_kernel<<<nw + 2, 256, 0, st>>>(ctx->d_slab, ctx->d_slab_cnt, ctx->d_slab_base, d_hits, max_hits);
-				BT_CUDA_TRY(cudaGetLastError());
-				BT_CUDA_TRY(cudaStreamSynchronize(st));
 				if ((int64_t)total > max_hits)
 					return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
 				return BTBB_B200_OK;
 			}
 			/* a slab overflowed (very dense hits): fall through to the generic path */
 		} else {
-			/* slab mode not taken: the launch above already produced the unordered list in d_tmp */
-			BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
-			BT_CUDA_TRY(cudaStreamSynchronize(st));
-			if (total >> 62)
-				return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
+			total = ctx->h_res[0];
 			*n_hits = (int64_t)total;
 			int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 			btbb_b200_hit *res = NULL;
@@ -954,7 +989,7 @@ int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed,
 	btbb_b200_hit *first = (passes & 1) ? ctx->d_tmp : d_hits;
 	btbb_b200_hit *other = (passes & 1) ? d_hits : ctx->d_tmp;
 	BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
-	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, 0, st, NULL, packed);
+	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, ctx->hit_bias, st, NULL, packed);
 	if (rc) return rc;
 	BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
@@ -968,6 +1003,38 @@ int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed,
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
 	if ((int64_t)total > max_hits)
 		return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
+	return BTBB_B200_OK;
+}
+
+int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits, cudaStream_t st)
+{
+	*n_hits = 0;
+	int rc = bt_find_ac_dev_begin(ctx, d_stream, packed, search_length, lap, max_ac_errors, d_hits, max_hits, st);
+	if (rc) return rc;
+	return bt_find_ac_dev_end(ctx, n_hits);
+}
+
+extern "C" int btbb_b200_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+					   uint32_t lap, int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits,
+					   void *cuda_stream)
+{
+	if (!ctx || (!d_hits && max_hits > 0) || (!d_stream && search_length > 0) ||
+	    search_length < 0 || max_hits < 0 || (lap != BTBB_B200_LAP_ANY && lap > 0xffffffu))
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_begin: bad arguments");
+	return bt_find_ac_dev_begin(ctx, d_stream, 0, search_length, lap, max_ac_errors, d_hits, max_hits, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int btbb_b200_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
+{
+	if (!ctx || !n_hits) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_end: bad arguments");
+	return bt_find_ac_dev_end(ctx, n_hits);
+}
+
+extern "C" int btbb_b200_set_offset_bias(btbb_b200_ctx *ctx, int64_t bias)
+{
+	if (!ctx) return btbb_b200_set_error(BTBB_B200_EINVAL, "set_offset_bias: bad arguments");
+	ctx->hit_bias = bias;
 	return BTBB_B200_OK;
 }
 

@@ -73,3 +73,78 @@ def gather_hits(local_hits, group=None, concat=True):
         return body, counts
     out = torch.cat([body[r, :c] for r, c in enumerate(counts)], dim=0)
     return out, counts
+
+
+class PeerGather:
+    """The same all-gather of hit records, over NVLink peer memory with the COPY ENGINES.
+
+    The scan kernel owns every SM (one persistent CTA per SM, all registers and shared memory),
+    so an NCCL collective can only run after it, and the gather shows up in the step time.  Here
+    every rank owns a symmetric-memory buffer of `world` slots (x 2 generations); a rank pushes its
+    records -- a header record carrying the count, then the records -- into its slot on every
+    peer with plain device-to-device copies on a side stream.  Those are DMA transfers: they
+    overlap the NEXT step's scan completely.  One symmetric-memory barrier per generation (a
+    one-block kernel on the side stream) tells every rank that all slots have landed.
+
+    start(local_hits) enqueues the exchange of one step; finish() makes the current stream wait
+    for the most recent one and returns (slots [world, cap, 16], counts).
+    """
+
+    def __init__(self, cap_records, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.cap = int(cap_records)
+        self.dev = device
+        shape = (2, self.world, self.cap + 1, 16)
+        self.buf = symm.empty(shape, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.peers = [self.hdl.get_buffer(r, shape, torch.uint8) for r in range(self.world)]
+        self.hdr = torch.zeros((2, 16), dtype=torch.uint8).pin_memory()      # header record per generation
+        self.stream = torch.cuda.Stream(device=device)
+        self.sent = [None, None]          # event per generation: its header has left pinned memory
+        self.gen = 0
+        self.last = None
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def start(self, local_hits):
+        """local_hits: [n, 16] records, complete on the current stream (the caller has synchronised
+        it or will not touch it until two more start() calls).  Everything enqueued here is a copy
+        (host-to-device for the header, device-to-device for the records), so it does not need an
+        SM while the next scan holds all of them; only the closing barrier is a (one-block) kernel."""
+        n = int(local_hits.shape[0])
+        if n > self.cap:
+            raise ValueError("PeerGather: more records than the slots hold")
+        g = self.gen
+        self.gen ^= 1
+        if self.sent[g] is not None:
+            self.sent[g].synchronize()             # the header of two steps ago has been read
+        self.hdr[g].view(torch.int64)[0] = n
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.stream):
+            for r in range(self.world):
+                slot = self.peers[r][g, self.rank]
+                slot[0].copy_(self.hdr[g], non_blocking=True)
+                if n:
+                    slot[1: n + 1].copy_(local_hits, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.sent[g] = ev
+            self.hdl.barrier(channel=g)            # every rank's copies of this generation have landed
+        self.last = g
+
+    def wait_sent(self, g):
+        """Host-side wait until generation g's copies have left this rank (its source buffer may
+        then be overwritten)."""
+        if self.sent[g] is not None:
+            self.sent[g].synchronize()
+
+    def finish(self):
+        g = self.last
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+        slots = self.buf[g]
+        counts = slots.view(torch.int64)[:, 0, 0].tolist()
+        return slots[:, 1:], counts
