@@ -399,8 +399,11 @@ static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t sear
 	}
 	cudaStream_t st = ctx->copy_stream[0];
 	int64_t n_b = 0;
+	const int64_t saved_bias = ctx->hit_bias;      /* btbb_b200_set_offset_bias is for the device entry points */
+	ctx->hit_bias = 0;
 	rc = bt_find_ac_dev_impl(ctx, reinterpret_cast<const uint8_t *>(ctx->d_packed), 1, search_length - split, lap,
 				 max_ac_errors, ctx->d_tmp2, room, &n_b, st);
+	ctx->hit_bias = saved_bias;
 	if (rc == BTBB_B200_EOVERFLOW) overflow = true;
 	else if (rc) return rc;
 	const int64_t have_b = n_b < room ? n_b : room;

@@ -224,6 +224,42 @@ def test_packed_ingest_matches_oracle(gpu_ctx2, orc, n):
         assert got == want.tobytes(), (n, hex(lap), k)
 
 
+def test_begin_end_halves_and_offset_bias(gpu_ctx2, orc):
+    """btbb_b200_find_ac_dev == _begin + _end; the offset bias shifts every reported offset; one
+    pending call per context."""
+    import torch
+    assert orc.orc_init(2) == 0
+    rng = np.random.default_rng(4242)
+    n = 500_003
+    s = rng.integers(0, 2, n + 63, dtype=np.uint8)
+    util.plant_syncwords(s, rng, 120, 2)
+    want = util.find_all(orc, "orc", s, n, B.LAP_ANY, 2)
+    d = torch.from_numpy(s).cuda()
+    cap = 4096
+    d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    for lap in (B.LAP_ANY, int(want[0]["lap"])):
+        ref = want if lap == B.LAP_ANY else util.find_all(orc, "orc", s, n, lap, 2)
+        gpu_ctx2.find_ac_dev_begin(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=lap, k=2)
+        with pytest.raises(B.BtbbError):
+            gpu_ctx2.find_ac_dev_begin(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=lap, k=2)
+        cnt, rc = gpu_ctx2.find_ac_dev_end()
+        assert rc == 0 and d_hits[:cnt].cpu().numpy().tobytes() == ref.tobytes()
+    with pytest.raises(B.BtbbError):
+        gpu_ctx2.find_ac_dev_end()                      # nothing pending
+    try:
+        gpu_ctx2.set_offset_bias(10**11)
+        cnt, rc = gpu_ctx2.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, k=2)
+        got = d_hits[:cnt].cpu().numpy().reshape(-1).view(B.HIT_DTYPE).copy()
+        assert rc == 0 and cnt == len(want)
+        assert np.array_equal(got["offset"], want["offset"] + 10**11)
+        got["offset"] -= 10**11
+        assert got.tobytes() == want.tobytes()
+        h = gpu_ctx2.find_ac_host(s, n, B.LAP_ANY, 2)   # the host entry point is not biased
+        assert h.tobytes() == want.tobytes()
+    finally:
+        gpu_ctx2.set_offset_bias(0)
+
+
 @pytest.mark.parametrize("k_init", [3, 4])
 def test_packed_and_byte_ingest_with_larger_tables(product_lib, k_init):
     """Tables for 3 / 4 errors take the bulk kernel's global-memory map variants, for both input
