@@ -1,30 +1,29 @@
 /*
- * scan_v7.cuh -- the bulk promiscuous access-code scan, fourth generation.
+ * scan_v7.cuh -- the bulk promiscuous access-code scan, fourth generation (the shipped kernel).
  *
  * Same decision per window as promiscuous_packet_search (bluetooth_packet.c:368-420) and the
  * same skeleton as scan_v4.cuh (warp-autonomous 4096-symbol strips, 256-bit loads, DP4A pack,
  * bit-sliced Barker filter, five branch-free in-place candidates per word, a per-warp queue
- * for the rest).  v4 ran at 80 % of the ALU pipe (LOP3 / SHF / PRMT / BMSK issue at half
- * rate) with the FMA pipe at 12 %, so v7 moves every piece of a candidate's work that has an
- * integer-multiply form over to the FMA pipe and shortens what has to stay:
+ * for the rest).  v4 ran at 80 % of the ALU pipe (LOP3 / SHF / PRMT / BMSK issue every second
+ * cycle) with the FMA pipe at 12 %; v7 shortens a candidate's ALU work and moves what has a cheap
+ * integer-multiply form to the FMA pipe:
  *
- *   enumerate  the candidate mask is kept bit-reversed; lowest set bit b = c & -c, where -c and
- *              c - b are IMADs.  b = 2^(31-q) for the candidate at bit q;
- *   window     (W * b) >> 32 = W >> (q + 1): the filter works on syndrome bits 1..32, whose
- *              identity part is window bits 1..32, so the two words it
- *              needs -- window bits 1..32 and 33..64 -- are two IMAD.HI + two IMAD on the
- *              lane's three stream words as they are (WIN = 1), instead of FLO + BMSK + two
- *              funnel shifts (WIN = 0, kept for A/B runs);
- *   syndrome   window bits 41..48 / 49..56 are bytes 1 / 2 of the second word: tables B / C are
- *              lane-private with a 256-byte entry pitch and share pages, so an index is ONE
- *              byte permute, prmt(hiF, 4 lane) = (byte << 8) | 4 lane.  Table A over bits
- *              34..40 either keeps the 128-byte pitch (TA = 0: one mask, one IMAD) or is
- *              stored with every entry twice at a 256-byte pitch (TA = 1: byte 0 of that word
- *              is bits 33..40 and bit 33 only reaches syndrome bit 33, so it too is one byte
- *              permute; the map shrinks to 32 KiB to make room);
+ *   syndrome   the filter works on syndrome bits 1..32, whose identity part is window bits 1..32;
+ *              the 24 window bits above, 33..56, are then bytes 0..2 of the second window word,
+ *              so with the lane's words pre-shifted by one the two window words are two funnel
+ *              shifts and a table index is ONE byte permute, prmt(hi, 4 lane) = (byte << 8) |
+ *              4 lane.  Tables B / C (bits 41..48 / 49..56) are lane-private with a 256-byte entry
+ *              pitch and share pages.  Table A over bits 34..40 either keeps a 128-byte pitch
+ *              (TA = 0: one mask, one IMAD) or is stored with every entry twice at a 256-byte
+ *              pitch (TA = 1, shipped: byte 0 is bits 33..40 and bit 33 only reaches syndrome
+ *              bit 33, so it too is one byte permute; the map shrinks to 32 KiB to make room);
  *   map        the first-level map is addressed by BYTE (address = the top 16 / 15 bits of the
- *              value, one shift, ld.shared.u8), the byte is replicated by an IMAD so that the
+ *              value, one LEA.HI, ld.shared.u8), the byte is replicated by an IMAD so that the
  *              shift by the raw value (mod 32) lands on bit (value & 7);
+ *   enumerate  candidate bit b by FLO + BMSK, c - b and the hit mask update as IMADs (WIN = 0,
+ *              shipped).  WIN = 1 keeps the mask bit-reversed (b = c & -c) and extracts the
+ *              windows as (W * b) >> 32 with IMAD.HI + IMAD instead of funnel shifts: lighter on
+ *              the ALU pipe but slower, because IMAD.HI issues every FOURTH cycle (tools/ibench.cu);
  *   halo       the 64 symbols after the strip are loaded with the strip (two byte loads per
  *              lane, two ballots) instead of by two lanes after the pack, which put a full
  *              memory round trip on every strip's critical path;
@@ -32,7 +31,10 @@
  *              beyond the fifth of a word in the per-warp queue, whose all-lanes-busy consumer
  *              runs both map levels and parks the rare survivors for the exact test.
  *
- * Shared memory by absolute shared-window address, see layout<TA>.
+ * Template parameters: WIN (window extraction), NSLOTS (in-place candidates per word), TA (table A
+ * / map layout), M2G (0: both maps in shared memory, tables for <= 2 errors; 1: second level in
+ * global memory, 3 errors; 2: FIRST level in global memory, 4 / 5 errors), PACKED (input already
+ * 32 symbols per word).  Shared memory by absolute shared-window address, see layout<TA>.
  */
 #pragma once
 
