@@ -69,3 +69,42 @@ def test_host_pack_bit_order_and_limit(product_lib):
             pad = (-(n - first)) % 32
             want = np.packbits(np.concatenate([s[first:], np.zeros(pad, dtype=np.uint8)]), bitorder="little").view("<u4")
             assert (out == want).all(), (n, first)
+
+
+C_CALLER = r"""
+/* what an existing libbtbb caller does: include the installed headers, link with -lbtbb */
+#include <stdio.h>
+#include <stdlib.h>
+#include "btbb.h"
+#include "btbb_b200.h"
+
+int main(void)
+{
+	btbb_b200_ctx *ctx = NULL;
+	btbb_b200_sieve pn;
+	btbb_b200_hit hit;
+	int rc = btbb_b200_create(0, 2, &ctx);
+	/* sync word of LAP 0x9e8b33 (SURVEY.md 8a4) through the classic surface: a pure host helper */
+	unsigned long long sw = (unsigned long long)btbb_gen_syncword(0x9e8b33);
+	printf("%d %d %d %llx %s\n", rc, (int)sizeof(hit), (int)sizeof(pn), sw, btbb_get_release());
+	if (ctx) btbb_b200_destroy(ctx);
+	return 0;
+}
+"""
+
+
+def test_c99_caller_compiles_links_and_runs(product_lib, tmp_path):
+    """The public headers are plain C and a C program links against libbtbb.so.1 by its SONAME --
+    the reference's own integration path (lib/libbtbb.pc.in: -lbtbb)."""
+    import subprocess
+    import torch
+    src = tmp_path / "caller.c"
+    src.write_text(C_CALLER)
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(B.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(util.ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:libbtbb.so.1", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    rc, hit_size, sieve_size, sw = int(out[0]), int(out[1]), int(out[2]), out[3]
+    assert hit_size == 16 and sieve_size == 160 and sw == "4e7a2cce331a3ae2"
+    assert rc == (0 if torch.cuda.is_available() else -2)

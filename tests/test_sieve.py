@@ -101,3 +101,39 @@ def test_gpu_sieve_in_two_calls_and_empty_groups(gpu_ctx2, orc):
     st1, rv1 = gpu_ctx2.uap_sieve_host(stream, pkts[:cut], gs[: g_cut + 1], np.zeros(g_cut, dtype=B.SIEVE_DTYPE))
     w1, wr1 = util.sieve_run(orc, "orc", stream, pkts[:cut], gs[: g_cut + 1])
     assert st1.tobytes() == w1.tobytes() and rv1.tobytes() == wr1.tobytes()
+
+
+def test_oracle_sieve_random_entry_states_vs_reference():
+    """Arbitrary piconet states on entry (half-eliminated candidate lists, packet counters next to
+    the 1000-packet limit, AFH flags, a UAP that is already known): the restatement must track the
+    reference's btbb_uap_from_header from any of them."""
+    if not util.have_ref():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    O, R = util.oracle(), util.ref()
+    stream, pkts, gs, laps, truth = util.sieve_case(n_slots=500, n_laps=5, ber=0.004, seed=41, mix=("ID", "HV1", "DM1"))
+    rng = np.random.default_rng(2718)
+    for trial in range(40):
+        st = np.zeros(len(gs) - 1, dtype=B.SIEVE_DTYPE)
+        for g in range(len(st)):
+            flags = 0
+            for bit, p in ((2, 0.15), (4, 0.15), (5, 0.1), (9, 0.0), (10, 0.6), (11, 0.3), (12, 0.3)):
+                if rng.random() < p:
+                    flags |= 1 << bit
+            st[g]["flags"] = flags
+            st[g]["first_pkt_time"] = rng.integers(0, 1 << 20)
+            st[g]["clk_offset"] = rng.integers(0, 64)
+            st[g]["packets_observed"] = rng.choice([0, 1, 7, 998, 999, 1000])
+            st[g]["total_packets_observed"] = rng.integers(0, 3000)
+            st[g]["uap"] = rng.integers(0, 256)
+            cand = rng.integers(0, 256, 64).astype(np.int16)
+            cand[rng.random(64) < 0.5] = -1
+            if rng.random() < 0.5:                      # make the true candidate plausible now and then
+                uap, clk0 = truth[laps[g]]
+                cand[(clk0 + int(st[g]["first_pkt_time"])) & 63] = uap
+            st[g]["clock6_candidates"] = cand
+            st[g]["afh_map"] = rng.integers(0, 256, 10)
+            st[g]["used_channels"] = int(np.unpackbits(st[g]["afh_map"]).sum())
+        a_st, a_rv = util.sieve_run(O, "orc", stream, pkts, gs, states=st)
+        b_st, b_rv = util.sieve_run(R, "ref", stream, pkts, gs, states=st)
+        assert a_rv.tobytes() == b_rv.tobytes(), trial
+        assert a_st.tobytes() == b_st.tobytes(), trial
