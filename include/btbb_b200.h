@@ -216,6 +216,31 @@ int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t str
 			     const int64_t *group_start, int64_t n_groups,
 			     btbb_b200_sieve *states, int8_t *rv);
 
+/*
+ * BR/EDR capture records (pcap, DLT 255) from batch results: the bytes btbb_pcap_create_file /
+ * btbb_pcap_append_packet (pcap.c:74-100, 176-209; record layout pcap-common.h:84-97) write,
+ * serialised from btbb_b200_hit + btbb_b200_decoded instead of from a btbb_packet.  meta carries
+ * what the reference takes from its arguments and from btbb_packet_set_data / _set_transport /
+ * _set_modulation.  Host formatting only.  A packet whose payload decode failed (rv < 2) gets
+ * zero payload bytes (the reference emits what its decoder left in pkt->payload).
+ */
+typedef struct btbb_b200_pcap_meta {
+	uint64_t ns;          /* timestamp, nanoseconds */
+	int8_t   sigdbm;      /* signal power */
+	int8_t   noisedbm;    /* noise power */
+	uint8_t  channel;     /* rf channel (btbb_packet_get_channel) */
+	uint8_t  transport;   /* BTBB_TRANSPORT_* */
+	uint8_t  modulation;  /* BTBB_MOD_* */
+	uint8_t  pad[3];
+} btbb_b200_pcap_meta;
+
+/* 24-byte file header; returns the bytes written or -1 */
+int64_t btbb_b200_pcap_file_header(uint8_t *out, int64_t cap);
+/* records for n packets; returns the bytes they take (written only when they fit in cap; out may be NULL) */
+int64_t btbb_b200_pcap_bredr_records(const btbb_b200_hit *hits, const btbb_b200_decoded *dec,
+				     const btbb_b200_pcap_meta *meta, int64_t n,
+				     uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap);
+
 /* ---- synthetic capture generator (SURVEY.md 8d "Synthetic input"; test/bench data only) ---- */
 typedef struct btbb_b200_synth_cfg {
 	uint64_t seed;          /* 0xB200B7BB by default */

@@ -48,6 +48,9 @@ PKTIN_DTYPE = np.dtype([("offset", "<i8"), ("length", "<i4"), ("clkn", "<u4"), (
 SIEVE_DTYPE = np.dtype([("flags", "<u4"), ("first_pkt_time", "<u4"), ("clk_offset", "<i4"), ("packets_observed", "<i4"),
                         ("total_packets_observed", "<i4"), ("uap", "u1"), ("used_channels", "u1"), ("afh_map", "u1", (10,)),
                         ("clock6_candidates", "<i2", (64,))])
+PCAP_META_DTYPE = np.dtype([("ns", "<u8"), ("sigdbm", "i1"), ("noisedbm", "i1"), ("channel", "u1"), ("transport", "u1"),
+                            ("modulation", "u1"), ("pad", "u1", (3,))])
+assert PCAP_META_DTYPE.itemsize == 16
 SIEVE_NOT_CALLED = -2
 F_UAP_VALID, F_CLK6_VALID, F_GOT_FIRST_PACKET = 1 << 2, 1 << 4, 1 << 10
 assert SIEVE_DTYPE.itemsize == 160
@@ -77,6 +80,8 @@ _PROTOS = {
     "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "btbb_b200_pcap_file_header": (_i64, [_vp, _i64]),
+    "btbb_b200_pcap_bredr_records": (_i64, [_vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64]),
     "btbb_b200_synth_host": (_int, [C.POINTER(SynthCfg), _vp]),
     "btbb_b200_synth_dev": (_int, [C.POINTER(SynthCfg), _vp, _vp]),
     "btbb_b200_synth_planted": (_int, [C.POINTER(SynthCfg), _i64, C.POINTER(Planted)]),
@@ -134,6 +139,20 @@ def synth_cfg(n_symbols, stride=10000, n_laps=64, ber=0.0, mix=("DM1", "DM3", "D
         m |= 1 << KIND[k]
     return SynthCfg(seed=seed, n_symbols=n_symbols, first_symbol=first_symbol, stride=stride, n_laps=n_laps,
                     ber_q32=min(int(ber * 2 ** 32), 2 ** 32 - 1), packet_mix=m, fixed_lap=fixed_lap, reserved=1 if piconets else 0)
+
+
+def pcap_bredr(hits, dec, meta, reflap=LAP_ANY, refuap=0xFF):
+    """File header + records as bytes (btbb_b200_pcap_file_header / _bredr_records)."""
+    assert hits.dtype == HIT_DTYPE and dec.dtype == DECODED_DTYPE and meta.dtype == PCAP_META_DTYPE
+    assert len(hits) == len(dec) == len(meta)
+    L = lib()
+    need = L.btbb_b200_pcap_bredr_records(hits.ctypes.data, dec.ctypes.data, meta.ctypes.data, len(hits), reflap, refuap, None, 0)
+    buf = np.zeros(24 + need, dtype=np.uint8)
+    assert L.btbb_b200_pcap_file_header(buf.ctypes.data, 24) == 24
+    got = L.btbb_b200_pcap_bredr_records(hits.ctypes.data, dec.ctypes.data, meta.ctypes.data, len(hits), reflap, refuap,
+                                         buf.ctypes.data + 24, need)
+    assert got == need
+    return buf.tobytes()
 
 
 def synth_host(cfg):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libbtbb.so.1")
-SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "sieve.cu", "synth.cu", "compat.cu", "host_pack.cpp"]
+SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "sieve.cu", "synth.cu", "compat.cu", "host_pack.cpp", "pcap_out.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,81 @@
+/*
+ * pcap_out.cpp -- BR/EDR capture records from batch results: the bytes
+ * btbb_pcap_create_file / btbb_pcap_append_packet (pcap.c:74-100, 176-209) write for a packet,
+ * serialised from the records the kernels produce (btbb_b200_hit + btbb_b200_decoded) instead
+ * of from a btbb_packet.  Pure host formatting, little-endian on the wire as in
+ * pcap-common.h:84-97 (DLT 255, LINKTYPE_BLUETOOTH_BREDR_BB).
+ *
+ * Known gap: for a packet whose payload decode FAILED (rv < 2) the reference still emits the
+ * pkt->payload bytes its decoder left behind, while btbb_b200_decoded carries payload bytes only
+ * for rv >= 2; such a record comes out with the right length and zero payload bytes.
+ */
+#include <string.h>
+#include "../../include/btbb_b200.h"
+
+namespace {
+
+const uint16_t F_DEWHITENED = 0x0001, F_SIGPOWER_VALID = 0x0002, F_NOISEPOWER_VALID = 0x0004, F_REFLAP_VALID = 0x0010,
+	       F_PAYLOAD_PRESENT = 0x0020, F_REFUAP_VALID = 0x0080;      /* pcap-common.h:63-76 */
+const uint32_t MAX_PAYLOAD = 400;                                     /* BREDR_MAX_PAYLOAD */
+const int64_t BB_HEADER = 22;                                         /* pcap_bluetooth_bredr_bb_header without the payload */
+
+inline void le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+inline void le32(uint8_t *p, uint32_t v) { le16(p, v); le16(p + 2, v >> 16); }
+
+}  // namespace
+
+/* the 24-byte file header of btbb_pcap_create_file (pcap.c:49-68, 79-80): nanosecond magic,
+ * version 2.4, snaplen 400, DLT 255.  Returns the bytes written, or -1 if cap is too small. */
+extern "C" int64_t btbb_b200_pcap_file_header(uint8_t *out, int64_t cap)
+{
+	if (!out || cap < 24) return -1;
+	le32(out, 0xa1b23c4du); le16(out + 4, 2); le16(out + 6, 4);
+	le32(out + 8, 0); le32(out + 12, 0); le32(out + 16, MAX_PAYLOAD); le32(out + 20, 255);
+	return 24;
+}
+
+/* n records of btbb_pcap_append_packet (pcap.c:176-209).  Returns the bytes the records take;
+ * they are written only if that fits in cap (out may be NULL to ask for the size). */
+extern "C" int64_t btbb_b200_pcap_bredr_records(const btbb_b200_hit *hits, const btbb_b200_decoded *dec,
+						const btbb_b200_pcap_meta *meta, int64_t n,
+						uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap)
+{
+	if (n < 0 || (n > 0 && (!hits || !dec || !meta))) return -1;
+	int64_t need = 0;
+	for (int64_t i = 0; i < n; i++) {
+		int64_t len = dec[i].payload_length;
+		if (len < 0) len = 0;
+		if (len > (int64_t)MAX_PAYLOAD) len = MAX_PAYLOAD;
+		need += 16 + BB_HEADER + len;
+	}
+	if (!out || need > cap) return need;
+	uint8_t *p = out;
+	for (int64_t i = 0; i < n; i++) {
+		const btbb_b200_pcap_meta &m = meta[i];
+		int64_t caplen = dec[i].payload_length;
+		if (caplen < 0) caplen = 0;
+		if (caplen > (int64_t)MAX_PAYLOAD) caplen = MAX_PAYLOAD;
+		const uint32_t rec = (uint32_t)(BB_HEADER + caplen);
+		uint16_t flags = F_DEWHITENED | F_SIGPOWER_VALID;
+		if (m.noisedbm < m.sigdbm) flags |= F_NOISEPOWER_VALID;
+		if (reflap != BTBB_B200_LAP_ANY) flags |= F_REFLAP_VALID;
+		if (refuap != 0xff) flags |= F_REFUAP_VALID;             /* UAP_ANY, btbb.h:96 */
+		if (caplen) flags |= F_PAYLOAD_PRESENT;
+		le32(p, (uint32_t)(m.ns / 1000000000ull)); le32(p + 4, (uint32_t)(m.ns % 1000000000ull));
+		le32(p + 8, rec); le32(p + 12, rec);
+		p += 16;
+		p[0] = m.channel; p[1] = (uint8_t)m.sigdbm; p[2] = (uint8_t)m.noisedbm; p[3] = hits[i].ac_errors;
+		p[4] = (uint8_t)((m.transport << 4) | m.modulation);
+		p[5] = 0;                                                   /* corrected header bits: "TODO" upstream */
+		le16(p + 6, 0);                                             /* corrected payload bits: likewise */
+		le32(p + 8, hits[i].lap);
+		le32(p + 12, (reflap & 0xffffffu) | ((uint32_t)refuap << 24));
+		le32(p + 16, dec[i].header_packed);
+		le16(p + 20, flags);
+		p += BB_HEADER;
+		/* btbb_get_payload_packed: payload_length bytes; the record carries 344, the rest is zero */
+		for (int64_t j = 0; j < caplen; j++) p[j] = j < 344 ? dec[i].payload[j] : 0;
+		p += caplen;
+	}
+	return need;
+}

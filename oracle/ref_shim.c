@@ -256,3 +256,39 @@ void ref_uap_sieve(char *stream, int64_t stream_length, const ref_pkt_in *pkts, 
 	close(saved); close(devnull);
 }
 
+/* ---- pcap BR/EDR emission: the reference's own btbb_pcap_create_file / btbb_pcap_append_packet
+ * (pcap.c, compiled as a further translation unit) on packets decoded by the reference.
+ * For packet i: symbols at stream + offset[i] (length[i]), found with lap[i] / ac_errors[i],
+ * decoded with clkn[i] / uap[i], logged with the given timestamps and powers.  rv[i] receives
+ * header_ok ? btbb_decode_payload's value : -1. ---- */
+typedef struct { uint64_t ns; int8_t sigdbm, noisedbm; uint8_t channel, transport, modulation, pad[3]; } ref_pcap_meta;
+
+int ref_pcap_bredr(const char *path, char *stream, int64_t stream_length, const ref_hit *hits, const ref_pkt_in *pkts,
+		   const ref_pcap_meta *meta, int64_t n, uint32_t reflap, uint8_t refuap, int32_t *rv)
+{
+	btbb_pcap_handle *h = NULL;
+	int64_t i;
+	static char zero[1];
+	if (btbb_pcap_create_file(path, &h)) return -1;
+	for (i = 0; i < n; i++) {
+		btbb_packet *p = btbb_packet_new();
+		int length = pkts[i].length > 3125 ? 3125 : pkts[i].length, ok, r = -1;
+		if (pkts[i].offset < 0 || pkts[i].offset >= stream_length) length = 0;
+		else if (pkts[i].offset + length > stream_length) length = (int)(stream_length - pkts[i].offset);
+		p->LAP = hits[i].lap; p->ac_errors = hits[i].ac_errors; p->flags = 0;
+		btbb_packet_set_flag(p, BTBB_WHITENED, pkts[i].whitened);
+		btbb_packet_set_data(p, length > 0 ? stream + pkts[i].offset : zero, length, meta[i].channel, pkts[i].clkn << 1);
+		btbb_packet_set_uap(p, pkts[i].uap);
+		btbb_packet_set_flag(p, BTBB_CLK6_VALID, 1);
+		btbb_packet_set_transport(p, meta[i].transport);
+		btbb_packet_set_modulation(p, meta[i].modulation);
+		ok = btbb_decode_header(p);
+		if (ok) r = btbb_decode_payload(p);
+		if (rv) rv[i] = r;
+		btbb_pcap_append_packet(h, meta[i].ns, meta[i].sigdbm, meta[i].noisedbm, reflap, refuap, p);
+		btbb_packet_unref(p);
+	}
+	btbb_pcap_close(h);
+	return 0;
+}
+

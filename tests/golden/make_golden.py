@@ -180,7 +180,38 @@ def gen_sieve():
     return out
 
 
+def gen_pcap():
+    """Digests of the files the reference's btbb_pcap_create_file / btbb_pcap_append_packet write for
+    the cases of tests/test_pcap.py -> tests/golden/pcap.json."""
+    import hashlib
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import test_pcap
+    R = util.ref()
+    R.ref_pcap_bredr.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_uint32, C.c_uint8, C.c_void_p]
+    out = {}
+    for name, kw in sorted(test_pcap.CASES.items()):
+        stream, hits, pkts, meta = test_pcap.build_case(**kw)
+        dec = test_pcap.oracle_records(stream, pkts)
+        keep = test_pcap.well_defined(dec)
+        for reflap, refuap in ((B.LAP_ANY, 0xFF), (0x9E8B33, 0x42)):
+            h, p, m = hits[keep].copy(), pkts[keep].copy(), meta[keep].copy()
+            rv = np.zeros(len(h), dtype=np.int32)
+            path = os.path.join("/tmp", f"golden_{os.getpid()}.pcap").encode()
+            assert R.ref_pcap_bredr(path, stream.ctypes.data, len(stream), h.ctypes.data, p.ctypes.data, m.ctypes.data,
+                                    len(h), reflap, refuap, rv.ctypes.data) == 0
+            data = open(path.decode(), "rb").read()
+            os.remove(path.decode())
+            out[f"{name}/{reflap:x}/{refuap:x}"] = {"shape": [int(keep.sum()), len(data)],
+                                                   "sha256": hashlib.sha256(data).hexdigest(), "kept_of": len(keep)}
+    json.dump(out, open(os.path.join(HERE, "pcap.json"), "w"), indent=1)
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pcap":
+        print(json.dumps(gen_pcap()))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sieve":
         print(json.dumps(gen_sieve()))
         sys.exit(0)
@@ -196,4 +227,5 @@ if __name__ == "__main__":
     json.dump(gen_decode(), open(os.path.join(HERE, "decode.json"), "w"), indent=0)
     json.dump(gen_noise_types(), open(os.path.join(HERE, "noise_types.json"), "w"), indent=0)
     gen_sieve()
+    gen_pcap()
     print("golden fixtures written to", HERE)
