@@ -83,11 +83,10 @@ class PeerGather:
     every rank owns a symmetric-memory buffer of `world` slots (x 2 generations); a rank pushes its
     records -- a header record carrying the count, then the records -- into its slot on every
     peer with plain device-to-device copies on a side stream.  Those are DMA transfers: they
-    overlap the NEXT step's scan completely.  One symmetric-memory barrier per generation (a
-    one-block kernel on the side stream) tells every rank that all slots have landed.
+    overlap the NEXT step's scan completely.  No kernel is involved, so nothing waits for an SM.
 
-    start(local_hits) enqueues the exchange of one step; finish() makes the current stream wait
-    for the most recent one and returns (slots [world, cap, 16], counts).
+    start(local_hits) enqueues the exchange of one step; finish() completes the most recent one on
+    every rank (host-side wait + one NCCL barrier) and returns (slots [world, cap, 16], counts).
     """
 
     def __init__(self, cap_records, device, group=None):
@@ -114,7 +113,7 @@ class PeerGather:
         """local_hits: [n, 16] records, complete on the current stream (the caller has synchronised
         it or will not touch it until two more start() calls).  Everything enqueued here is a copy
         (host-to-device for the header, device-to-device for the records), so it does not need an
-        SM while the next scan holds all of them; only the closing barrier is a (one-block) kernel."""
+        SM while the next scan holds all of them."""
         n = int(local_hits.shape[0])
         if n > self.cap:
             raise ValueError("PeerGather: more records than the slots hold")
@@ -133,7 +132,6 @@ class PeerGather:
             ev = torch.cuda.Event()
             ev.record(self.stream)
             self.sent[g] = ev
-            self.hdl.barrier(channel=g)            # every rank's copies of this generation have landed
         self.last = g
 
     def wait_sent(self, g):
@@ -143,8 +141,13 @@ class PeerGather:
             self.sent[g].synchronize()
 
     def finish(self):
+        """Complete the most recent exchange on every rank: wait until this rank's copies have left,
+        then meet the other ranks (one NCCL barrier) -- after it, every slot of the generation has
+        landed everywhere.  Between start() calls nothing synchronises the ranks: slots of older
+        generations may be overwritten by ranks that run ahead, only the latest one is read."""
         g = self.last
-        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+        self.stream.synchronize()
+        dist.barrier(self.group)
         slots = self.buf[g]
         counts = slots.view(torch.int64)[:, 0, 0].tolist()
         return slots[:, 1:], counts
