@@ -623,6 +623,8 @@ static int do_decode_payload(opkt *p, int clock)
 	return rv;
 }
 
+static int g_emit_raw;      /* orc_decode_one_raw: payload bytes as the decoder left them, whatever rv says */
+
 static void emit(const opkt *p, int header_ok, int rv, btbb_b200_decoded *o)
 {
 	int i;
@@ -632,7 +634,7 @@ static void emit(const opkt *p, int header_ok, int rv, btbb_b200_decoded *o)
 	o->hec = p->hec; o->llid = p->llid; o->flow = p->flow; o->has_payload = p->has_payload;
 	o->payload_header_length = p->phl; o->payload_length = p->plen;
 	o->header_packed = bits_le(p->hdr, 18);
-	if (rv >= 2 && p->plen > 0 && p->plen <= 344)
+	if ((rv >= 2 || g_emit_raw) && p->plen > 0 && p->plen <= 344)
 		for (i = 0; i < p->plen; i++)
 			o->payload[i] = (uint8_t)bits_le(p->pay + 8 * i, 8);
 }
@@ -660,6 +662,16 @@ void orc_decode_one(const char *symbols, int length, uint32_t clkn, uint8_t uap,
 	}
 	if (ok) rv = do_decode_payload(&p, (int)clkn);
 	emit(&p, ok, rv, out);
+}
+
+/* as orc_decode_one, but payload[] holds what the reference's decoders leave in pkt->payload even
+ * when the decode fails (what btbb_pcap_append_packet logs); not thread-safe (test helper) */
+void orc_decode_one_raw(const char *symbols, int length, uint32_t clkn, uint8_t uap,
+			int whitened, btbb_b200_decoded *out)
+{
+	g_emit_raw = 1;
+	orc_decode_one(symbols, length, clkn, uap, whitened, out);
+	g_emit_raw = 0;
 }
 
 void orc_try_clock_one(const char *symbols, int length, int clock, int whitened,

@@ -39,6 +39,8 @@ int      orc_header_present(const char *symbols, int length);
 
 void     orc_decode_one(const char *symbols, int length, uint32_t clkn, uint8_t uap,
 			int whitened, btbb_b200_decoded *out);
+void     orc_decode_one_raw(const char *symbols, int length, uint32_t clkn, uint8_t uap,
+			    int whitened, btbb_b200_decoded *out);
 void     orc_try_clock_one(const char *symbols, int length, int clock, int whitened,
 			   btbb_b200_decoded *out);
 void     orc_uap_sieve(const char *stream, int64_t stream_length, const btbb_b200_pkt_in *pkts, int64_t n_pkts,

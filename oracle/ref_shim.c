@@ -166,6 +166,29 @@ void ref_decode_one(char *symbols, int length, uint32_t clkn, uint8_t uap, int w
 	btbb_packet_unref(p);
 }
 
+/* as ref_decode_one, but payload[] holds pkt->payload as the decoders left it, whatever rv says
+ * (what btbb_pcap_append_packet logs) */
+void ref_decode_one_raw(char *symbols, int length, uint32_t clkn, uint8_t uap, int whitened, ref_decoded *out)
+{
+	btbb_packet *p = btbb_packet_new();
+	int i;
+	memset(out, 0, sizeof(*out));
+	p->LAP = 0; p->flags = 0;
+	btbb_packet_set_flag(p, BTBB_WHITENED, whitened);
+	btbb_packet_set_data(p, symbols, length, 0, clkn << 1);
+	btbb_packet_set_uap(p, uap);
+	btbb_packet_set_flag(p, BTBB_CLK6_VALID, 1);
+	btbb_packet_set_flag(p, BTBB_HAS_PAYLOAD, 0);
+	out->header_ok = btbb_decode_header(p);
+	if (out->header_ok)
+		out->rv = btbb_decode_payload(p);
+	fill_decoded(p, out);
+	if (p->payload_length > 0 && p->payload_length <= 344)
+		for (i = 0; i < p->payload_length; i++)
+			out->payload[i] = air_to_host8(&p->payload[i * 8], 8);
+	btbb_packet_unref(p);
+}
+
 /* try_clock + crc_check for one clock candidate (SURVEY 3.4 inner loop) */
 void ref_try_clock_one(char *symbols, int length, int clock, int whitened, ref_decoded *out)
 {

@@ -46,6 +46,7 @@ def oracle():
         L.orc_table_entries.restype = C.c_long
         L.orc_decode_one.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.orc_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_decode_one_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.orc_header_present.argtypes = [C.c_void_p, C.c_int]
         L.orc_uap_sieve.restype = None
         L.orc_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -78,6 +79,7 @@ def ref():
         L.ref_whitening_index.restype = C.c_uint8
         L.ref_decode_one.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.ref_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_decode_one_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.ref_header_present.argtypes = [C.c_void_p, C.c_int]
         L.ref_uap_sieve.restype = None
         L.ref_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -96,6 +98,13 @@ def find_all(L, prefix, stream, n, lap, k, cap=1 << 20):
 def decode_one(L, prefix, stream, off, length, clk, uap, whitened=1):
     d = np.zeros(1, dtype=B.DECODED_DTYPE)
     getattr(L, prefix + "_decode_one")(stream[off:].ctypes.data, length, clk, uap, whitened, d.ctypes.data)
+    return d[0]
+
+
+def decode_one_raw(L, prefix, stream, off, length, clk, uap, whitened=1):
+    """decode_one with the payload bytes as the decoder left them, whatever rv says."""
+    d = np.zeros(1, dtype=B.DECODED_DTYPE)
+    getattr(L, prefix + "_decode_one_raw")(stream[off:].ctypes.data, length, clk, uap, whitened, d.ctypes.data)
     return d[0]
 
 
