@@ -801,3 +801,49 @@ void orc_uap_sieve(const char *stream, int64_t stream_length, const btbb_b200_pk
 	}
 }
 
+/* ---- hop sequence: gen_hops (bluetooth_piconet.c:311-362) in closed form,
+ * one entry per sequence index (= CLK27-1), so that any range can be produced independently --
+ * the shape a one-thread-per-entry kernel needs.  address = (UAP << 24 | LAP) & 0xfffffff
+ * (gen_hop_pattern, :371-372); afh_map == NULL means all 79 channels (precalc, :171-193). ---- */
+static int hop_perm5(int z, int p_high, int p_low)           /* perm5, :258-290 */
+{
+	static const int i1[14] = {0, 2, 1, 3, 0, 1, 0, 3, 1, 0, 2, 1, 0, 1};
+	static const int i2[14] = {1, 3, 2, 4, 4, 3, 2, 4, 4, 3, 4, 3, 3, 2};
+	int p = (p_high << 9) | p_low, i;
+	for (i = 13; i >= 0; i--)
+		if ((p >> i) & 1) {
+			int a = (z >> i1[i]) & 1, b = (z >> i2[i]) & 1;
+			if (a != b) z ^= (1 << i1[i]) | (1 << i2[i]);
+		}
+	return z;
+}
+
+void orc_hop_sequence(uint32_t address, const uint8_t *afh_map, int64_t first, int64_t n, uint8_t *out)
+{
+	int bank[79], used = 0, i;
+	int64_t idx;
+	const int a1 = (address >> 23) & 0x1f, b = (address >> 19) & 0x0f;                      /* address_precalc, :196-215 */
+	const int c1 = ((address >> 4) & 0x10) + ((address >> 3) & 0x08) + ((address >> 2) & 0x04) +
+		       ((address >> 1) & 0x02) + (address & 0x01);
+	const int d1 = (address >> 10) & 0x1ff;
+	const int e = ((address >> 7) & 0x40) + ((address >> 6) & 0x20) + ((address >> 5) & 0x10) +
+		      ((address >> 4) & 0x08) + ((address >> 3) & 0x04) + ((address >> 2) & 0x02) + ((address >> 1) & 0x01);
+	for (i = 0; i < 79; i++) {
+		int chan = (i * 2) % 79;
+		if (!afh_map) bank[i] = chan;
+		else if (afh_map[chan / 8] & (1 << (chan % 8))) bank[used++] = chan;
+	}
+	for (idx = first; idx < first + n; idx++) {
+		const int y1 = (int)(idx & 1);
+		const int64_t pair = idx >> 1;
+		const int x = (int)(pair & 31), k = (int)((pair >> 5) & 511), j = (int)((pair >> 14) & 31), ii = (int)((pair >> 19) & 31);
+		const int a = a1 ^ ii, c = (c1 ^ j) ^ (y1 ? 0x1f : 0), d = d1 ^ k;
+		const uint32_t f = (uint32_t)(16 * (pair >> 5)) % 79;
+		const int perm = hop_perm5(((x + a) % 32) ^ b, c, d);
+		if (afh_map)          /* note: f_dash = (base_f % 79) % used here, unlike single_hop (:425) */
+			out[idx - first] = (uint8_t)bank[(perm + e + (int)(f % (uint32_t)used) + 32 * y1) % used];
+		else
+			out[idx - first] = (uint8_t)bank[(perm + e + (int)f + 32 * y1) % 79];
+	}
+}
+

@@ -45,4 +45,5 @@ void     orc_try_clock_one(const char *symbols, int length, int clock, int white
 			   btbb_b200_decoded *out);
 void     orc_uap_sieve(const char *stream, int64_t stream_length, const btbb_b200_pkt_in *pkts, int64_t n_pkts,
 		       const int64_t *group_start, int64_t n_groups, btbb_b200_sieve *states, int8_t *rv);
+void     orc_hop_sequence(uint32_t address, const uint8_t *afh_map, int64_t first, int64_t n, uint8_t *out);
 #endif

@@ -315,3 +315,28 @@ int ref_pcap_bredr(const char *path, char *stream, int64_t stream_length, const 
 	return 0;
 }
 
+/* ---- hop sequence: the reference's gen_hop_pattern (bluetooth_piconet.c:365-377) for one address,
+ * entries [first, first + n) of its 2^27-entry table copied out.  afh_map == NULL: all channels. ---- */
+void ref_hop_sequence(uint32_t address, const uint8_t *afh_map, int64_t first, int64_t n, uint8_t *out)
+{
+	btbb_piconet *pn = btbb_piconet_new();
+	int i, saved, devnull;
+	pn->LAP = address & 0xffffff;
+	pn->UAP = (address >> 24) & 0xff;
+	if (afh_map) {
+		btbb_piconet_set_flag(pn, BTBB_IS_AFH, 1);
+		for (i = 0; i < 10; i++) pn->afh_map[i] = afh_map[i];
+		pn->used_channels = 0;
+		for (i = 0; i < 79; i++) pn->used_channels += (afh_map[i / 8] >> (i % 8)) & 1;
+	} else
+		pn->used_channels = 79;     /* gen_hops divides by it even without AFH (:356); any packet seen makes it > 0 */
+	fflush(stdout);
+	saved = dup(1); devnull = open("/dev/null", O_WRONLY); dup2(devnull, 1);
+	gen_hop_pattern(pn);
+	fflush(stdout);
+	dup2(saved, 1); close(saved); close(devnull);
+	memcpy(out, pn->sequence + first, (size_t)n);
+	free(pn->sequence);
+	btbb_piconet_unref(pn);
+}
+

@@ -208,7 +208,28 @@ def gen_pcap():
     return out
 
 
+def gen_hops():
+    """Digests of windows of the reference's 2^27-entry hop table (gen_hop_pattern) for the addresses
+    of tests/test_hops.py -> tests/golden/hops.json."""
+    import hashlib
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import test_hops
+    R = util.ref()
+    out = {}
+    for name, (addr, afh) in sorted(test_hops.CASES.items()):
+        full = test_hops._seq(R, "ref", addr, afh, 0, 1 << 27)
+        d = {"full": hashlib.sha256(full.tobytes()).hexdigest()}
+        for first, n in test_hops.WINDOWS:
+            d[f"{first}+{n}"] = hashlib.sha256(full[first:first + n].tobytes()).hexdigest()
+        out[name] = d
+    json.dump(out, open(os.path.join(HERE, "hops.json"), "w"), indent=1)
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "hops":
+        print(json.dumps(gen_hops()))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pcap":
         print(json.dumps(gen_pcap()))
         sys.exit(0)
@@ -228,4 +249,5 @@ if __name__ == "__main__":
     json.dump(gen_noise_types(), open(os.path.join(HERE, "noise_types.json"), "w"), indent=0)
     gen_sieve()
     gen_pcap()
+    gen_hops()
     print("golden fixtures written to", HERE)

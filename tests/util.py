@@ -48,6 +48,8 @@ def oracle():
         L.orc_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_decode_one_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.orc_header_present.argtypes = [C.c_void_p, C.c_int]
+        L.orc_hop_sequence.restype = None
+        L.orc_hop_sequence.argtypes = [C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_uap_sieve.restype = None
         L.orc_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         _oracle = L
@@ -81,6 +83,8 @@ def ref():
         L.ref_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_decode_one_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.ref_header_present.argtypes = [C.c_void_p, C.c_int]
+        L.ref_hop_sequence.restype = None
+        L.ref_hop_sequence.argtypes = [C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.ref_uap_sieve.restype = None
         L.ref_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         _ref = L
