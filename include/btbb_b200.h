@@ -211,6 +211,13 @@ int btbb_b200_uap_sieve_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t
 			    const btbb_b200_pkt_in *d_pkts, int64_t n_pkts,
 			    const int64_t *d_group_start, int64_t n_groups,
 			    btbb_b200_sieve *d_states, int8_t *d_rv, void *cuda_stream);
+/* Host helper: stable grouping of hit records by LAP (what get_piconet(LAP),
+ * bluetooth_piconet.c:820-840, does packet by packet in survey mode).  order[0..n) receives the
+ * hit indices sorted by (LAP, arrival order); group_start (n + 1 entries, or NULL) the group
+ * boundaries in that order; laps (n entries, or NULL) each group's LAP.  Returns the number of
+ * groups, or -1. */
+int64_t btbb_b200_group_by_lap(const btbb_b200_hit *hits, int64_t n, int64_t *order,
+			       int64_t *group_start, uint32_t *laps);
 int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
 			     const btbb_b200_pkt_in *pkts, int64_t n_pkts,
 			     const int64_t *group_start, int64_t n_groups,

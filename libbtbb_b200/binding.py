@@ -80,6 +80,7 @@ _PROTOS = {
     "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "btbb_b200_group_by_lap": (_i64, [_vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_pcap_file_header": (_i64, [_vp, _i64]),
     "btbb_b200_pcap_bredr_records": (_i64, [_vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64]),
     "btbb_b200_synth_host": (_int, [C.POINTER(SynthCfg), _vp]),
@@ -139,6 +140,18 @@ def synth_cfg(n_symbols, stride=10000, n_laps=64, ber=0.0, mix=("DM1", "DM3", "D
         m |= 1 << KIND[k]
     return SynthCfg(seed=seed, n_symbols=n_symbols, first_symbol=first_symbol, stride=stride, n_laps=n_laps,
                     ber_q32=min(int(ber * 2 ** 32), 2 ** 32 - 1), packet_mix=m, fixed_lap=fixed_lap, reserved=1 if piconets else 0)
+
+
+def group_by_lap(hits):
+    """btbb_b200_group_by_lap: (order, group_start, laps)."""
+    assert hits.dtype == HIT_DTYPE
+    n = len(hits)
+    order = np.zeros(n, dtype=np.int64)
+    gs = np.zeros(n + 1, dtype=np.int64)
+    laps = np.zeros(max(n, 1), dtype=np.uint32)
+    g = lib().btbb_b200_group_by_lap(hits.ctypes.data, n, order.ctypes.data, gs.ctypes.data, laps.ctypes.data)
+    assert g >= 0
+    return order, gs[: g + 1].copy(), laps[:g].copy()
 
 
 def pcap_bredr(hits, dec, meta, reflap=LAP_ANY, refuap=0xFF):

@@ -10,6 +10,8 @@
  * for rv >= 2; such a record comes out with the right length and zero payload bytes.
  */
 #include <string.h>
+#include <algorithm>
+#include <numeric>
 #include "../../include/btbb_b200.h"
 
 namespace {
@@ -79,3 +81,26 @@ extern "C" int64_t btbb_b200_pcap_bredr_records(const btbb_b200_hit *hits, const
 	}
 	return need;
 }
+
+/* Host helper for the per-piconet entry points (btbb_b200_uap_sieve_*): stable grouping of hit
+ * records by LAP, i.e. what get_piconet(LAP) (bluetooth_piconet.c:820-840) does one packet at a
+ * time in survey mode.  order[0..n) receives the hit indices sorted by (LAP, arrival order),
+ * group_start[0..g] the group boundaries in that order, laps[0..g) each group's LAP (both may
+ * be NULL to only count).  Returns the number of groups g (<= n), or -1 on bad arguments. */
+extern "C" int64_t btbb_b200_group_by_lap(const btbb_b200_hit *hits, int64_t n, int64_t *order,
+					  int64_t *group_start, uint32_t *laps)
+{
+	if (n < 0 || (n > 0 && (!hits || !order))) return -1;
+	std::iota(order, order + n, (int64_t)0);
+	std::stable_sort(order, order + n, [&](int64_t a, int64_t b) { return hits[a].lap < hits[b].lap; });
+	int64_t g = 0;
+	for (int64_t i = 0; i < n; i++)
+		if (i == 0 || hits[order[i]].lap != hits[order[i - 1]].lap) {
+			if (group_start) group_start[g] = i;
+			if (laps) laps[g] = hits[order[i]].lap;
+			g++;
+		}
+	if (group_start) group_start[g] = n;
+	return g;
+}
+

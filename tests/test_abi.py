@@ -108,3 +108,19 @@ def test_c99_caller_compiles_links_and_runs(product_lib, tmp_path):
     rc, hit_size, sieve_size, sw = int(out[0]), int(out[1]), int(out[2]), out[3]
     assert hit_size == 16 and sieve_size == 160 and sw == "4e7a2cce331a3ae2"
     assert rc == (0 if torch.cuda.is_available() else -2)
+
+
+def test_group_by_lap_is_a_stable_grouping(product_lib):
+    import numpy as np
+    rng = np.random.default_rng(8)
+    for n in (0, 1, 2, 17, 5000):
+        hits = np.zeros(n, dtype=B.HIT_DTYPE)
+        hits["offset"] = np.sort(rng.integers(0, 10**9, n))
+        hits["lap"] = rng.choice(np.array([0x9E8B33, 0x123456, 0xFFFFFF, 0, 77], dtype=np.uint32), n)
+        order, gs, laps = B.group_by_lap(hits)
+        want = np.argsort(hits["lap"], kind="stable")
+        assert np.array_equal(order, want)
+        assert list(laps) == sorted(set(hits["lap"].tolist())) and gs[0] == 0 and gs[-1] == n if n else len(gs) == 1
+        for g, lap in enumerate(laps):
+            grp = hits[order[gs[g]:gs[g + 1]]]
+            assert (grp["lap"] == lap).all() and (np.diff(grp["offset"]) >= 0).all()
