@@ -75,6 +75,10 @@ typedef struct btbb_b200_pkt_in {
 #define BTBB_B200_MODE_CRC_CHECK   3   /* crc_check(clkn & 63, pkt) alone, packet_type/UAP as given (:708-769) */
 #define BTBB_B200_MODE_RAW         16  /* + n: one type decoder without crc_check's post-filter:
                                           0 fhs, 1 DM, 2 DH, 3 EV3, 4 EV4, 5 EV5, 6 HV (:783-1174) */
+/* OR-ed into a mode: payload[] carries what the reference's decoders leave in pkt->payload even
+ * when the decode FAILED (rv < 2) -- the bytes btbb_pcap_append_packet logs (pcap.c:173-209) --
+ * instead of zeros.  Bits no decoder wrote read 0 (a freshly allocated btbb_packet). */
+#define BTBB_B200_MODE_FLAG_RAW_PAYLOAD 0x100
 
 typedef struct btbb_b200_ctx btbb_b200_ctx;
 
@@ -166,6 +170,25 @@ int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t st
 int btbb_b200_decode_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
 			  const btbb_b200_pkt_in *pkts, int64_t n, int mode,
 			  btbb_b200_decoded *out);
+
+/* BTBB_B200_MODE_TRY_CLOCKS with a compact result: one 16-bit word per (packet, clock) at
+ * d_tc[64 * packet + clock] -- the UAP try_clock derived (bluetooth_packet.c:1178-1195) in the low
+ * byte, the class of crc_check's return value (:708-769) above it: 0, 1, 2 as returned, 3 for 10,
+ * 4 for 1000.  This is what the UAP sieve consumes; 128 bytes per packet instead of 23 808. */
+int btbb_b200_try_clocks_compact_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+				     const btbb_b200_pkt_in *d_pkts, int64_t n, uint16_t *d_tc, void *cuda_stream);
+
+/*
+ * One packet through the same chain ON THE HOST (decode_core.h compiled for the CPU): the small-call
+ * path of the classic single-packet surface (btbb_decode_header / btbb_decode_payload / try_clock /
+ * crc_check ..., bluetooth_packet.c:1178-1317), where a caller hands over at most 3125 symbols per
+ * call and a kernel launch would cost far more than the arithmetic ("Drop-in
+ * latency").  Same records as btbb_b200_decode_host for one packet: out holds 1 record, 64 in
+ * BTBB_B200_MODE_TRY_CLOCKS.  `type` is used by modes >= 2 only.  The batch entry points above
+ * never take this route.
+ */
+int btbb_b200_decode_smallcall(const char *symbols, int length, uint32_t clkn, uint8_t uap,
+			       int whitened, uint8_t type, int mode, btbb_b200_decoded *out);
 
 /* btbb_header_present (bluetooth_packet.c:1371-1408) for n packets; d_present[n] gets 0/1. */
 int btbb_b200_header_present_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,

@@ -77,6 +77,8 @@ _PROTOS = {
     "btbb_b200_find_ac_host": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64)]),
     "btbb_b200_decode_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp, _vp]),
     "btbb_b200_decode_host": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp]),
+    "btbb_b200_try_clocks_compact_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "btbb_b200_decode_smallcall": (_int, [_vp, _int, _u32, C.c_uint8, _int, C.c_uint8, _int, _vp]),
     "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
@@ -166,6 +168,17 @@ def pcap_bredr(hits, dec, meta, reflap=LAP_ANY, refuap=0xFF):
                                          buf.ctypes.data + 24, need)
     assert got == need
     return buf.tobytes()
+
+
+MODE_DECODE, MODE_TRY_CLOCKS, MODE_PAYLOAD, MODE_CRC_CHECK, MODE_RAW, MODE_FLAG_RAW_PAYLOAD = 0, 1, 2, 3, 16, 0x100
+
+
+def decode_smallcall(symbols, length, clkn=0, uap=0, whitened=1, ptype=0, mode=0):
+    """btbb_b200_decode_smallcall: the chain for one packet on the host (1 record, 64 in mode 1)."""
+    assert symbols.dtype == np.uint8 and symbols.flags.c_contiguous
+    out = np.zeros(64 if (mode & 0xff) == MODE_TRY_CLOCKS else 1, dtype=DECODED_DTYPE)
+    check(lib().btbb_b200_decode_smallcall(symbols.ctypes.data, length, clkn, uap, whitened, ptype, mode, out.ctypes.data))
+    return out
 
 
 def synth_host(cfg):

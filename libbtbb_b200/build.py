@@ -4,52 +4,80 @@
 
 The shared object lands in libbtbb_b200/lib/libbtbb.so.1 (SONAME libbtbb.so.1, the
 name upstream installs, lib/src/CMakeLists.txt:43-52) so it travels with the source
-snapshot to the GPU box.
+snapshot to the GPU box.  Sources are compiled one object each (in parallel, rebuilt only
+when the source or a header changed) and linked; libbtbb.a (upstream's optional static
+library, lib/src/CMakeLists.txt:54-63) is archived from the same objects.
 """
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libbtbb.so.1")
-SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "sieve.cu", "synth.cu", "compat.cu", "host_pack.cpp", "pcap_out.cpp"]
+STATIC = os.path.join(LIBDIR, "libbtbb.a")
+SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "decode_tables.cpp", "decode_host.cpp", "sieve.cu",
+           "hops.cu", "synth.cu", "compat.cu", "host_pack.cpp", "pcap_out.cpp", "sharded.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fvisibility=default", "--shared",
-    "-Xlinker", "-soname=libbtbb.so.1",
-]
+CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+          "-Xcompiler", "-fPIC,-fvisibility=default"]
+LDFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xlinker", "-soname=libbtbb.so.1"]
 
 
-def _stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+def _headers_mtime():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps += [os.path.join(HERE, "..", "include", f) for f in ("btbb_b200.h", "btbb.h")]
     deps.append(os.path.abspath(__file__))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return max(os.path.getmtime(d) for d in deps)
+
+
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
 def build(force=False, verbose=False, ptxas_verbose=False):
-    if not force and not _stale():
-        return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if ptxas_verbose else [])
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libbtbb.so.1")
-    if ptxas_verbose or verbose:
-        sys.stderr.write(r.stdout + r.stderr)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr_t = _headers_mtime()
+    jobs, objs = [], []
+    for s in _sources():
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJDIR, s + ".o")
+        objs.append(obj)
+        if force or ptxas_verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            cmd = [NVCC] + CFLAGS + (["-Xptxas", "-v"] if ptxas_verbose else []) + ["-c", src, "-o", obj]
+            jobs.append((s, cmd))
+
+    def run(job):
+        name, cmd = job
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return name, r
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for name, r in ex.map(run, jobs):
+                if r.returncode != 0:
+                    sys.stderr.write(r.stdout + r.stderr)
+                    raise RuntimeError(f"nvcc failed compiling {name}")
+                if ptxas_verbose or verbose:
+                    sys.stderr.write(r.stdout + r.stderr)
+    if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [NVCC] + LDFLAGS + objs + ["-o", LIB]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed linking libbtbb.so.1")
+        if os.path.exists(STATIC):
+            os.remove(STATIC)
+        subprocess.run(["ar", "rcs", STATIC] + objs, check=False)
     return LIB
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True, ptxas_verbose="--ptxas-verbose" in sys.argv)
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_verbose="--ptxas-verbose" in sys.argv)
     print(LIB)

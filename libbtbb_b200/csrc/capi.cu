@@ -10,6 +10,7 @@
 #include <sched.h>
 #include <time.h>
 #include <atomic>
+#include <new>
 #include <thread>
 #include <vector>
 #include "capi_internal.h"
@@ -52,6 +53,8 @@ extern "C" int btbb_b200_create(int device, int max_ac_errors, btbb_b200_ctx **o
 	if (!ctx) return btbb_b200_set_error(BTBB_B200_ENOMEM, "create: out of host memory");
 	ctx->device = device;
 	ctx->sm_count = prop.multiProcessorCount;
+	ctx->host_lock = new (std::nothrow) std::mutex();
+	if (!ctx->host_lock) { free(ctx); return btbb_b200_set_error(BTBB_B200_ENOMEM, "create: out of host memory"); }
 	int rc = bt_tables_build(ctx, max_ac_errors);
 	if (rc == BTBB_B200_OK) {
 		e = cudaMalloc(&ctx->d_count, 2 * sizeof(unsigned long long));
@@ -80,6 +83,10 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_sieve_idx) cudaFree(ctx->d_sieve_idx);
 	if (ctx->d_sieve_cur) cudaFree(ctx->d_sieve_cur);
 	for (int i = 0; i < 2; i++) if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
+	if (ctx->d_dec_tables) cudaFree(ctx->d_dec_tables);
+	for (int i = 0; i < 4; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+	delete ctx->host_lock;
+	if (ctx->ev_reset) cudaEventDestroy(ctx->ev_reset);
 	if (ctx->d_slab) cudaFree(ctx->d_slab);
 	if (ctx->d_slab_cnt) cudaFree(ctx->d_slab_cnt);
 	if (ctx->d_slab_base) cudaFree(ctx->d_slab_base);
@@ -134,7 +141,12 @@ static int scan_host_prepare(btbb_b200_ctx *ctx, int64_t span, int64_t max_hits,
 			ctx->tmp2_cap = cap;
 		}
 	}
-	BT_CUDA_TRY(cudaMemset(ctx->d_count, first_key ? 0xff : 0, sizeof(unsigned long long)));
+	/* the scans run on the two non-blocking copy streams: reset the counter there, and make the
+	 * second stream wait for it */
+	BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, first_key ? 0xff : 0, sizeof(unsigned long long), ctx->copy_stream[0]));
+	if (!ctx->ev_reset) BT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_reset, cudaEventDisableTiming));
+	BT_CUDA_TRY(cudaEventRecord(ctx->ev_reset, ctx->copy_stream[0]));
+	BT_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream[1], ctx->ev_reset, 0));
 	*chunk_out = chunk;
 	return BTBB_B200_OK;
 }
@@ -169,7 +181,7 @@ static int scan_host_finish(btbb_b200_ctx *ctx, int64_t span, btbb_b200_hit *hit
 	*n_hits = (int64_t)total;
 	int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 	btbb_b200_hit *res = NULL;
-	int rc = bt_sort_hits(ctx, ctx->d_tmp, ctx->d_tmp2, have, bt_sort_passes(span), ctx->copy_stream[0], &res);
+	int rc = bt_sort_hits(ctx, ctx->d_tmp, ctx->d_tmp2, have, bt_sort_passes(span), 0, ctx->copy_stream[0], &res);
 	if (rc) return rc;
 	if (have > 0)
 		BT_CUDA_TRY(cudaMemcpyAsync(hits, res, (size_t)have * sizeof(btbb_b200_hit), cudaMemcpyDeviceToHost, ctx->copy_stream[0]));

@@ -3,6 +3,7 @@
 #define BTBB_B200_CAPI_INTERNAL_H
 
 #include <stdint.h>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "../../include/btbb_b200.h"
 
@@ -26,7 +27,7 @@ struct bt_pending {
 	int mode;
 	const uint8_t *d_stream;
 	int packed, max_ac_errors;
-	int64_t search_length, max_hits;
+	int64_t search_length, max_hits, bias;
 	uint32_t lap;
 	btbb_b200_hit *d_hits;
 	cudaStream_t st;
@@ -89,6 +90,11 @@ struct btbb_b200_ctx {
 	int64_t *d_sieve_idx;        /* UAP sieve: packets of the current round (sieve_cap entries) */
 	int64_t *d_sieve_cur;        /* UAP sieve: per-piconet cursor, then one 64-bit counter */
 	int64_t sieve_groups_cap;
+	void *d_dec_tables;          /* per-packet chain: device copy of btd_tables (decode_core.h) */
+	void *d_scratch[4];          /* grow-only device scratch of the host-buffer entry points */
+	size_t scratch_cap[4];
+	cudaEvent_t ev_reset;        /* host-buffer scan: the counter reset has been enqueued */
+	std::mutex *host_lock;       /* serialises the host-buffer entry points, which share the scratch above */
 };
 
 int btbb_b200_set_error(int code, const char *msg);
@@ -117,7 +123,7 @@ int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint3
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
 		   int64_t bias, cudaStream_t st);
 int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t have,
-		 int passes, cudaStream_t st, btbb_b200_hit **result);
+		 int passes, int64_t key_bias, cudaStream_t st, btbb_b200_hit **result);
 int bt_sort_passes(int64_t span);
 
 /* decode.cu */

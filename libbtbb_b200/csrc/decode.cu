@@ -1,481 +1,342 @@
 /*
  * decode.cu -- K4/K5: the per-packet chain  unfec13 -> unwhiten -> HEC  and
- * unfec23 / unwhiten / CRC  (bluetooth_packet.c:552-705, 708-1317) for a batch of
- * detected packets, one warp per packet.
+ * unfec23 / unwhiten / CRC  (bluetooth_packet.c:552-705, 708-1317) for a batch of detected
+ * packets, one warp per packet.  The arithmetic is decode_core.h (shared with the host path of
+ * the classic single-packet calls); this file is the warp-level plumbing around it:
  *
- * Everything that does not depend on the clock candidate is done once per packet by the
- * whole warp and parked in shared memory as packed bits:
- *   - the packet's symbols (ballot-packed, symbols past `length` read 0 like a fresh
- *     btbb_packet),
- *   - the FEC-1/3 header vote (unfec13 :552-568) and the HV1 payload vote,
- *   - every FEC-2/3 block from symbol 122 on (and from 202 on for DV, :914), corrected,
- *     with the index of the first uncorrectable block (unfec23 :585-649).
- * The clock-dependent tail (dewhiten :653-668, uap_from_hec :693-705, payload header
- * :821-895, CRC :671-690 byte-wise by table) then runs with one lane per CLK1-6 candidate
- * in mode 1 (try_clock + crc_check, :1178-1195 / :708-769) or on lane 0 in mode 0
- * (btbb_decode_header + btbb_decode_payload, :1198-1297).
+ *   ingest   128-bit loads from the 16-byte aligned base below the packet, 16 symbols -> 16 bits
+ *            with one multiply per 4 symbols, pairs of lanes combined by shuffle -> packed words
+ *            in shared memory (symbols past `length` read 0 like a fresh btbb_packet).  The header
+ *            part (512 symbols) comes first; it decides which packet types are in play and with
+ *            them how much of the packet is needed at all.
+ *   once per packet, independent of the clock: the FEC 1/3 votes (unfec13 :552-568), every
+ *            needed FEC 2/3 block (unfec23 :585-649; lane = block), and the CRC prefix tables of
+ *            each bit source (lane = run of bytes, XOR scan across lanes).
+ *   per clock  lane = CLK1-6 candidate (try_clock + crc_check, :1178-1195 / :708-769; two rounds of
+ *            32) or all lanes on the packet's own clock (btbb_decode_header + _payload,
+ *            :1198-1297).  A payload CRC is one table test; the length searches of EV3 / EV4 / EV5
+ *            and the 33 clocks of fhs are spread over the lanes (ballot = first match).
+ *   output   one 372-byte record per packet written as 93 coalesced words, or 64 records per
+ *            packet staged in shared memory, 32 at a time, and stored with one bulk copy
+ *            (cp.async.bulk shared -> global, 11 904 bytes), or the UAP sieve's 16-bit words.
  */
 #include <cuda_runtime.h>
 #include <string.h>
 #include "bt_math.h"
+#include "decode_core.h"
 #include "capi_internal.h"
+
+const btd_tables *btd_host_tables();
+int bt_decode_one_cpu(const char *symbols, int length, uint32_t clkn, uint8_t uap, int whitened, uint8_t type,
+		      int mode, btbb_b200_decoded *out);
 
 namespace {
 
-constexpr int WARPS = 4;
-constexpr int RAW_WORDS = 100;      /* 3200 >= 3125 symbols */
-constexpr int FEC_BLOCKS = 200;     /* (3125 - 122) / 15 */
-constexpr int FEC_WORDS = 64;       /* 200 * 10 bits */
+enum { OUT_ONE = 0, OUT_FULL64 = 1, OUT_TC16 = 2 };
+constexpr int REC_WORDS = (int)(sizeof(btbb_b200_decoded) / 4);      /* 93 */
+constexpr int STAGE_BYTES = 32 * (int)sizeof(btbb_b200_decoded);     /* 11 904 = 16 x 744 */
+constexpr int PKT_BYTES = (int)((sizeof(btd_pkt) + 15) & ~(size_t)15);
+constexpr int NIB_BYTES = BTD_LMAX * 2 * 16 * 2;
+constexpr int SMALL_BYTES = (int)((sizeof(btd_small_tables) + 15) & ~(size_t)15);
+constexpr unsigned FULL = 0xffffffffu;
+static_assert(sizeof(btbb_b200_decoded) == 372 && STAGE_BYTES % 16 == 0, "record layout");
+static_assert(NIB_BYTES % 16 == 0 && SMALL_BYTES % 16 == 0, "table layout");
 
-struct dec_tables {
-	uint32_t wseq[13];     /* whitening m-sequence from state 0x40, three periods */
-	uint8_t phase[64];     /* position in wseq where the LFSR state is 0x40 | clk */
-	uint16_t crc[256];     /* reflected CRC-16/CCITT byte table */
-	uint8_t fec_col[10];   /* parity column of each data bit */
-	uint8_t pad[2];
-};
-__constant__ dec_tables c_dec;
-
-struct warp_smem {
-	uint32_t raw[RAW_WORDS + 1];
-	uint32_t fec0[FEC_WORDS + 1];   /* corrected data bits, blocks from symbol 122 */
-	uint32_t fec80[FEC_WORDS + 1];  /* ... from symbol 202 (DV) */
-	uint32_t hv1[4];                /* FEC-1/3 vote of the 240 symbols at 122 */
-	uint32_t hdr;                   /* 18 voted header bits */
-	int hdr_ok, hv1_ok, fail0, fail80, length;
-};
-
-struct lane_state {
-	uint32_t uap, type, lt_addr, flags, hec, llid, flow, has_payload;
-	int phl, plen;
-	int src, pay_clk;    /* where the payload bytes come from, for the final emit */
-};
-enum { SRC_NONE = 0, SRC_FEC0, SRC_FEC80, SRC_RAW, SRC_HV1, SRC_FIRST8 };
-
-__device__ __forceinline__ uint32_t bits_at(const uint32_t *w, int pos, int n)
-{
-	uint32_t v = __funnelshift_r(w[pos >> 5], w[(pos >> 5) + 1], pos & 31);
-	return n >= 32 ? v : v & ((1u << n) - 1);
-}
-
-__device__ __forceinline__ uint32_t whiten_bits(const uint32_t *s_wseq, const uint8_t *s_phase,
-						int clk, int pos, int n, int whitened)
-{
-	if (!whitened) return 0;
-	int p = (s_phase[clk & 63] + pos) % 127;
-	return bits_at(s_wseq, p, n);
-}
-
-struct dec_ctx {
-	const warp_smem *ws;
-	const uint32_t *wseq;
-	const uint8_t *phase;
-	const uint16_t *crc;
-	int whitened;
+struct dec_args {
+	const uint8_t *stream;
+	int64_t stream_len;
+	const btbb_b200_pkt_in *pkts;
+	int64_t n;
+	int mode, raw_payload;
+	btbb_b200_decoded *out;
+	uint16_t *tc16;
+	const int64_t *idx;                  /* work item i is packet idx[i] (UAP sieve rounds) */
+	const unsigned long long *n_dev;     /* item count in device memory */
+	const btd_tables *tables;
 };
 
-__device__ uint32_t pay_byte(const dec_ctx &d, int src, int clk, int i)
+template <int OUT, int WARPS>
+constexpr int smem_bytes() { return SMALL_BYTES + NIB_BYTES + WARPS * (PKT_BYTES + (OUT == OUT_FULL64 ? STAGE_BYTES : 0)); }
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
-	uint32_t b;
-	switch (src) {
-	case SRC_FEC0:  b = bits_at(d.ws->fec0, 8 * i, 8); break;
-	case SRC_FEC80: b = bits_at(d.ws->fec80, 8 * i, 8); break;
-	case SRC_RAW:   b = bits_at(d.ws->raw, 122 + 8 * i, 8); break;
-	case SRC_HV1:   b = bits_at(d.ws->hv1, 8 * i, 8); break;
-	case SRC_FIRST8: b = bits_at(d.ws->raw, 122, 8); break;   /* EV3/EV5 quirk, :1036 */
-	default: b = 0;
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
+
+/* raw words [w_begin, w_end) (multiples of 16) from 16-symbol chunks of the aligned base */
+__device__ __forceinline__ void ingest(btd_pkt &P, const uint4 *base, int sh, int length, int w_begin, int w_end, int lane)
+{
+	for (int w0 = w_begin; w0 < w_end; w0 += 16) {
+		const int c = 2 * w0 + lane;
+		const uint32_t m = btd_chunk_mask(c, sh, length);
+		uint32_t h = 0;
+		if (m) {
+			const uint4 v = ld_stream(base + c);
+			h = btd_pack16(v.x, v.y, v.z, v.w) & m;
+		}
+		const uint32_t hi = __shfl_down_sync(FULL, h, 1);
+		if (!(lane & 1)) P.raw[w0 + (lane >> 1)] = h | (hi << 16);
 	}
-	return b ^ whiten_bits(d.wseq, d.phase, clk, 18 + 8 * i, 8, d.whitened);
 }
 
-__device__ __forceinline__ uint32_t crc_byte(const dec_ctx &d, uint32_t reg, uint32_t byte)
+/* FEC 2/3 blocks [0, nblk) from symbol `start`: lane = block; returns the first uncorrectable one */
+__device__ __forceinline__ int fec_blocks(const btd_pkt &P, uint32_t *dst, int start, int nblk, const uint8_t *col, int lane)
 {
-	return (reg >> 8) ^ d.crc[(reg ^ byte) & 0xff];
-}
-
-/* payload_crc (:772-781) for plen >= 2 */
-__device__ bool crc_matches(const dec_ctx &d, int src, int clk, int plen, uint32_t uap)
-{
-	uint32_t reg = bt_crc16_init(uap);
-	for (int i = 0; i < plen - 2; i++)
-		reg = crc_byte(d, reg, pay_byte(d, src, clk, i));
-	uint32_t chk = pay_byte(d, src, clk, plen - 2) | (pay_byte(d, src, clk, plen - 1) << 8);
-	return reg == chk;
-}
-
-/* fhs (:783-818) */
-__device__ int dec_fhs(const dec_ctx &d, lane_state &s, int clock)
-{
-	int size = d.ws->length - 122;
-	s.plen = 20;
-	if (size < 240) return 1;
-	if (d.ws->fail0 < 16) return 0;
-	s.src = SRC_FEC0; s.pay_clk = clock;
-	if (crc_matches(d, SRC_FEC0, clock, 20, s.uap)) return 1000;
-	for (int c = 32; c < 64; c++) {
-		s.pay_clk = c;
-		if (crc_matches(d, SRC_FEC0, c, 20, s.uap)) return 1000;
-	}
-	return 0;
-}
-
-/* decode_payload_header (:821-895); start80 selects the DV block alignment */
-__device__ int dec_pay_hdr(const dec_ctx &d, lane_state &s, int clock, int hbytes, int size, int fec, bool dv)
-{
-	int nb = hbytes * 8;
-	if (size < nb) return 0;
-	uint32_t ph;
-	if (fec) {
-		if (size < (hbytes == 2 ? 30 : 15)) return 0;
-		int need = hbytes == 2 ? 2 : 1;
-		if ((dv ? d.ws->fail80 : d.ws->fail0) < need) return 0;
-		ph = bits_at(dv ? d.ws->fec80 : d.ws->fec0, 0, nb);
-	} else
-		ph = bits_at(d.ws->raw, 122, nb);
-	ph ^= whiten_bits(d.wseq, d.phase, clock, 18, nb, d.whitened);
-	s.plen = hbytes == 2 ? (int)((ph >> 3) & 0x3ff) + 4 : (int)((ph >> 3) & 0x1f) + 3;
-	int maxlen;
-	switch (s.type) {
-	case 3: maxlen = 20; break;
-	case 4: maxlen = 30; break;
-	case 8: maxlen = 12; break;
-	case 10: maxlen = 125; break;
-	case 11: maxlen = 187; break;
-	case 14: maxlen = 228; break;
-	case 15: maxlen = 343; break;
-	default: maxlen = 0;
-	}
-	if (s.plen > maxlen) s.plen = maxlen;
-	s.llid = ph & 3;
-	s.flow = (ph >> 2) & 1;
-	s.phl = hbytes;
-	return 1;
-}
-
-/* DM (:898-958) */
-__device__ int dec_dm(const dec_ctx &d, lane_state &s, int clock)
-{
-	int size = d.ws->length - 122, hbytes = 2, maxlen;
-	bool dv = false;
-	switch (s.type) {
-	case 8: dv = true; size -= 80; hbytes = 1; maxlen = 12; break;
-	case 3: hbytes = 1; maxlen = 20; break;
-	case 10: maxlen = 125; break;
-	case 14: maxlen = 228; break;
-	default: return 0;
-	}
-	if (!dec_pay_hdr(d, s, clock, hbytes, size, 1, dv)) return 0;
-	if (s.plen > maxlen) return 1;
-	int nbits = s.plen * 8;
-	if (nbits > size) return 1;
-	if ((dv ? d.ws->fail80 : d.ws->fail0) < (nbits + 9) / 10) return 0;
-	s.src = dv ? SRC_FEC80 : SRC_FEC0; s.pay_clk = clock;
-	return crc_matches(d, s.src, clock, s.plen, s.uap) ? 10 : 2;
-}
-
-/* DH (:962-1011) */
-__device__ int dec_dh(const dec_ctx &d, lane_state &s, int clock)
-{
-	int size = d.ws->length - 122, hbytes = 2, maxlen;
-	switch (s.type) {
-	case 9: case 4: hbytes = 1; maxlen = 30; break;
-	case 11: maxlen = 187; break;
-	case 15: maxlen = 343; break;
-	default: return 0;
-	}
-	if (!dec_pay_hdr(d, s, clock, hbytes, size, 0, false)) return 0;
-	if (s.plen > maxlen) return 1;
-	int nbits = s.plen * 8;
-	if (nbits > size) return 1;
-	s.src = SRC_RAW; s.pay_clk = clock;
-	if (s.type == 9) return 2;
-	return crc_matches(d, SRC_RAW, clock, s.plen, s.uap) ? 10 : 2;
-}
-
-/* EV3 (:1013-1042) / EV5 (:1099-1128) with an incremental CRC */
-__device__ int dec_ev35(const dec_ctx &d, lane_state &s, int clock, int maxlength)
-{
-	int size = d.ws->length - 122;
-	uint32_t reg = bt_crc16_init(s.uap);   /* CRC over bytes [0, plen-2) */
-	s.src = SRC_FIRST8; s.pay_clk = clock;
-	for (s.plen = 0; s.plen < maxlength; s.plen++) {
-		if (s.plen * 8 + 8 > size) return 1;
-		if (s.plen > 2) {
-			reg = crc_byte(d, reg, pay_byte(d, SRC_FIRST8, clock, s.plen - 3));
-			uint32_t chk = pay_byte(d, SRC_FIRST8, clock, s.plen - 2) |
-				       (pay_byte(d, SRC_FIRST8, clock, s.plen - 1) << 8);
-			if (reg == chk) return 10;
+	const int nwords = (10 * nblk + 31) / 32 + 1;
+	for (int w = lane; w < nwords; w += 32) dst[w] = 0;
+	__syncwarp();
+	int fail = 1 << 20;
+	for (int b0 = 0; b0 < nblk; b0 += 32) {
+		const int b = b0 + lane;
+		const bool live = b < nblk;
+		uint32_t data = 0;
+		bool ok = true;
+		if (live) ok = btd_fec23_block(btd_bits(P.raw, P.sh + start + 15 * b, 15), col, &data);
+		const uint32_t badmask = __ballot_sync(FULL, live && !ok);
+		if (badmask && fail == (1 << 20)) fail = b0 + __ffs(badmask) - 1;
+		if (live && ok) {
+			const int pos = 10 * b;
+			atomicOr(&dst[pos >> 5], data << (pos & 31));
+			if ((pos & 31) > 22) atomicOr(&dst[(pos >> 5) + 1], data >> (32 - (pos & 31)));
 		}
 	}
-	return 2;
+	__syncwarp();
+	return fail;
 }
 
-/* EV4 (:1044-1097) with an incremental CRC */
-__device__ int dec_ev4(const dec_ctx &d, lane_state &s, int clock)
+/* dp[L] = XOR of the CRC weights of the first L bytes of a source: lane = run of bytes, XOR scan over lanes */
+__device__ __forceinline__ void build_dp(const btd_pkt &P, const uint16_t *nib, int src, int nbytes, uint16_t *dp, int lane)
 {
-	int size = d.ws->length - 122, syms = 0, bits = 0, blk = 0;
-	uint32_t reg = bt_crc16_init(s.uap);   /* CRC over bytes [0, plen-2) once plen >= 2 */
-	s.plen = 1;
-	s.src = SRC_FEC0; s.pay_clk = clock;
-	while (syms < 1470) {
-		if (syms + 15 > size) return 1;
-		if (d.ws->fail0 <= blk) return syms < 45 ? 0 : 1;
-		while (s.plen * 8 <= bits) {
-			if (s.plen >= 2) {
-				uint32_t chk = pay_byte(d, SRC_FEC0, clock, s.plen - 2) |
-					       (pay_byte(d, SRC_FEC0, clock, s.plen - 1) << 8);
-				if (reg == chk) return 10;
-				reg = crc_byte(d, reg, pay_byte(d, SRC_FEC0, clock, s.plen - 2));
-			}
-			/* plen == 1: the reference compares the CRC preload (low byte 0) with a word
-			 * whose bit 4 is the packet's own payload_length byte (=1): never equal */
-			s.plen++;
-		}
-		syms += 15; bits += 10; blk++;
+	if (nbytes <= 0) { if (lane == 0) dp[0] = 0; return; }
+	const int C = (nbytes + 31) >> 5;
+	const int j0 = lane * C, j1 = j0 + C < nbytes ? j0 + C : nbytes;
+	uint32_t acc = 0;
+	for (int j = j0; j < j1; j++) {
+		acc ^= btd_byte_weight(nib, j, btd_src_byte(P, src, j));
+		dp[j + 1] = (uint16_t)acc;
 	}
-	return 2;
-}
-
-/* HV (:1131-1174) */
-__device__ int dec_hv(const dec_ctx &d, lane_state &s, int clock)
-{
-	int size = d.ws->length - 122;
-	s.phl = 0;
-	if (size < 240) { s.plen = 0; return 1; }
-	switch (s.type) {
-	case 5:
-		if (!d.ws->hv1_ok) return 0;
-		s.plen = 10; s.has_payload = 1; s.src = SRC_HV1; s.pay_clk = clock;
-		break;
-	case 6:
-		if (d.ws->fail0 < 16) return 0;
-		s.plen = 20; s.has_payload = 1; s.src = SRC_FEC0; s.pay_clk = clock;
-		break;
-	case 7:
-		s.plen = 30; s.has_payload = 1; s.src = SRC_RAW; s.pay_clk = clock;
-		break;
-	}
-	return 2;
-}
-
-/* crc_check (:708-769) */
-__device__ int do_crc_check(const dec_ctx &d, lane_state &s, int clock)
-{
-	int rv = 1;
-	switch (s.type) {
-	case 2: rv = dec_fhs(d, s, clock); break;
-	case 8: case 3: case 10: case 14: rv = dec_dm(d, s, clock); break;
-	case 4: case 11: case 15: rv = dec_dh(d, s, clock); break;
-	case 7: rv = dec_ev35(d, s, clock, 32); break;
-	case 12: rv = dec_ev4(d, s, clock); break;
-	case 13: rv = dec_ev35(d, s, clock, 182); break;
-	case 5: rv = dec_hv(d, s, clock); break;
-	default: break;
-	}
-	if (rv == 0 && s.type != 2 && s.type != 3 && s.type != 5) return 1;
-	if (rv > 1 && (s.type == 7 || s.type == 13)) return 1;
-	return rv;
-}
-
-/* btbb_decode_payload (:1223-1297) */
-__device__ int do_decode_payload(const dec_ctx &d, lane_state &s, int clock)
-{
-	int rv = 0;
-	s.phl = 0;
-	switch (s.type) {
-	case 0: case 1: s.plen = 0; rv = 1; break;
-	case 2: rv = dec_fhs(d, s, clock); break;
-	case 3: case 8: case 10: case 14: rv = dec_dm(d, s, clock); break;
-	case 4: case 9: case 11: case 15: rv = dec_dh(d, s, clock); break;
-	case 5: case 6: rv = dec_hv(d, s, clock); break;
-	case 7:
-		rv = dec_ev35(d, s, clock, 32);
-		if (rv <= 1) rv = dec_hv(d, s, clock);
-		break;
-	case 12: rv = dec_ev4(d, s, clock); break;
-	case 13: rv = dec_ev35(d, s, clock, 182); break;
-	}
-	s.has_payload = 1;
-	return rv;
-}
-
-__device__ void emit_record(const dec_ctx &d, const lane_state &s, int header_ok, int rv,
-			    uint32_t header_packed, btbb_b200_decoded *o)
-{
-	o->header_ok = header_ok; o->rv = rv;
-	o->uap = (uint8_t)s.uap; o->type = (uint8_t)s.type; o->lt_addr = (uint8_t)s.lt_addr;
-	o->flags = (uint8_t)s.flags; o->hec = (uint8_t)s.hec; o->llid = (uint8_t)s.llid;
-	o->flow = (uint8_t)s.flow; o->has_payload = (uint8_t)s.has_payload;
-	o->payload_header_length = s.phl; o->payload_length = s.plen;
-	o->header_packed = header_packed;
-	int n = (rv >= 2 && s.plen > 0 && s.plen <= 344) ? s.plen : 0;
-	for (int i = 0; i < n; i++)
-		o->payload[i] = (uint8_t)pay_byte(d, s.src, s.pay_clk, i);
-	for (int i = n; i < 344; i++)
-		o->payload[i] = 0;
-}
-
-/* corrected data bits of one (15,10) block; false when the reference would give up */
-__device__ __forceinline__ bool fec23_block(uint32_t cw15, const uint8_t *col, uint32_t *data10)
-{
-	uint32_t data = cw15 & 0x3ff, diff = (cw15 >> 10) & 0x1f;
+	uint32_t inc = acc;
 	#pragma unroll
-	for (int i = 0; i < 10; i++)
-		if ((data >> i) & 1) diff ^= col[i];
-	if (diff & (diff - 1)) {
-		bool fixed = false;
-		#pragma unroll
-		for (int i = 0; i < 10; i++)
-			if (col[i] == diff) { data ^= 1u << i; fixed = true; }
-		if (!fixed) return false;
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(FULL, inc, d);
+		if (lane >= d) inc ^= t;
 	}
-	*data10 = data;
-	return true;
+	const uint32_t base = inc ^ acc;
+	for (int j = j0; j < j1; j++) dp[j + 1] ^= (uint16_t)base;
+	if (lane == 0) dp[0] = 0;
 }
 
-__global__ void __launch_bounds__(WARPS * 32) decode_kernel(const uint8_t *stream, int64_t stream_len,
-							     const btbb_b200_pkt_in *pkts, int64_t n, int mode,
-							     btbb_b200_decoded *out, uint16_t *tc16,
-							     const int64_t *idx, const unsigned long long *n_dev)
+/* first candidate in [lo, hi) that passes, all lanes working on the same search */
+__device__ __forceinline__ int coop_search(const btd_ctx &c, const btd_pkt &P, int pend, int clock, uint32_t uap,
+					   int lo, int hi, int lane)
 {
-	__shared__ warp_smem s_w[WARPS];
-	__shared__ uint32_t s_wseq[13];
-	__shared__ uint8_t s_phase[64];
-	__shared__ uint16_t s_crc[256];
-	__shared__ uint8_t s_col[16];
-	for (int i = threadIdx.x; i < 13; i += blockDim.x) s_wseq[i] = c_dec.wseq[i];
-	for (int i = threadIdx.x; i < 64; i += blockDim.x) s_phase[i] = c_dec.phase[i];
-	for (int i = threadIdx.x; i < 256; i += blockDim.x) s_crc[i] = c_dec.crc[i];
-	if (threadIdx.x < 10) s_col[threadIdx.x] = c_dec.fec_col[threadIdx.x];
+	for (int b = lo; b < hi; b += 32) {
+		const int cand = b + lane;
+		const bool ok = cand < hi && btd_cand_ok(c, P, pend, clock, uap, cand);
+		const uint32_t m = __ballot_sync(FULL, ok);
+		if (m) return b + __ffs(m) - 1;
+	}
+	return -1;
+}
+
+/* crc_check / decode_payload / one decoder for this lane's (clock, UAP, type); searches are shared */
+template <bool UNIFORM>
+__device__ __forceinline__ void evaluate(const btd_ctx &c, const btd_pkt &P, btd_lane &s, int kind, int lane)
+{
+	btd_eval_begin(c, P, s, kind);
+	int found = -1;
+	if (UNIFORM) {
+		if (s.pend) found = coop_search(c, P, s.pend, s.clock, s.uap, s.s_lo, s.s_hi, lane);
+	} else {
+		uint32_t pm = __ballot_sync(FULL, s.pend != BTD_PEND_NONE);
+		while (pm) {
+			const int o = __ffs(pm) - 1;
+			pm &= pm - 1;
+			const int pend = __shfl_sync(FULL, s.pend, o), clock = __shfl_sync(FULL, s.clock, o);
+			const uint32_t uap = __shfl_sync(FULL, s.uap, o);
+			const int lo = __shfl_sync(FULL, s.s_lo, o), hi = __shfl_sync(FULL, s.s_hi, o);
+			const int f = coop_search(c, P, pend, clock, uap, lo, hi, lane);
+			if (lane == o) found = f;
+		}
+	}
+	btd_eval_end(P, s, kind, found);
+}
+
+template <int OUT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	btd_small_tables *s_small = reinterpret_cast<btd_small_tables *>(smem);
+	uint16_t *s_nib = reinterpret_cast<uint16_t *>(smem + SMALL_BYTES);
+	{
+		const uint4 *g0 = reinterpret_cast<const uint4 *>(&a.tables->s);
+		uint4 *d0 = reinterpret_cast<uint4 *>(smem);
+		for (int i = threadIdx.x; i < (int)sizeof(btd_small_tables) / 16; i += blockDim.x) d0[i] = g0[i];
+		const uint4 *g1 = reinterpret_cast<const uint4 *>(a.tables->nib);
+		uint4 *d1 = reinterpret_cast<uint4 *>(smem + SMALL_BYTES);
+		for (int i = threadIdx.x; i < NIB_BYTES / 16; i += blockDim.x) d1[i] = g1[i];
+	}
 	__syncthreads();
 
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	warp_smem &ws = s_w[wid];
-	/* idx / n_dev (the UAP sieve's rounds, sieve.cu): work item i is packet idx[i], and the number
-	 * of items is read from device memory */
-	if (n_dev) n = (int64_t)*n_dev;
+	btd_pkt &P = *reinterpret_cast<btd_pkt *>(smem + SMALL_BYTES + NIB_BYTES + wid * PKT_BYTES);
+	uint32_t *stage = reinterpret_cast<uint32_t *>(smem + SMALL_BYTES + NIB_BYTES + WARPS * PKT_BYTES + wid * STAGE_BYTES);
+	if (lane == 0) P.raw[BTD_RAW_WORDS - 1] = 0;
+	btd_ctx c;
+	c.s = s_small; c.nib = s_nib; c.wp = a.tables->wp;
+	int64_t n = a.n;
+	if (a.n_dev) n = (int64_t)*a.n_dev;
+	const int mode = a.mode;
+
 	for (int64_t it = (int64_t)blockIdx.x * WARPS + wid; it < n; it += (int64_t)gridDim.x * WARPS) {
-		const int64_t p = idx ? idx[it] : it;
-		const btbb_b200_pkt_in in = pkts[p];
+		const int64_t p = a.idx ? a.idx[it] : it;
+		const btbb_b200_pkt_in in = a.pkts[p];
 		int length = in.length;
 		if (length > BT_MAX_SYMBOLS) length = BT_MAX_SYMBOLS;       /* btbb_packet_set_data :472 */
-		if (in.offset < 0 || in.offset >= stream_len) length = 0;
-		else if (in.offset + length > stream_len) length = (int)(stream_len - in.offset);
+		if (in.offset < 0 || in.offset >= a.stream_len) length = 0;
+		else if (in.offset + length > a.stream_len) length = (int)(a.stream_len - in.offset);
 		if (length < 0) length = 0;
-		const uint8_t *sym = stream + in.offset;
+		const uintptr_t addr = reinterpret_cast<uintptr_t>(a.stream) + (uintptr_t)(length > 0 ? in.offset : 0);
+		const int sh = (int)(addr & 15);
+		const uint4 *base = reinterpret_cast<const uint4 *>(addr - (uintptr_t)sh);
+		c.whitened = in.whitened;
 		__syncwarp();
-		/* ---- pack symbols ---- */
-		for (int w = 0; w <= RAW_WORDS; w++) {
-			int i = w * 32 + lane;
-			uint32_t b = (i < length) ? (sym[i] & 1u) : 0u;
-			uint32_t word = __ballot_sync(0xffffffffu, b);
-			if (lane == 0) ws.raw[w] = word;
-		}
-		if (lane == 0) ws.length = length;
+		if (lane == 0) { P.sh = sh; P.length = length; }
+		/* ---- header part: 512 symbols from the aligned base ---- */
+		ingest(P, base, sh, length, 0, 16, lane);
 		__syncwarp();
-		/* ---- FEC 1/3 votes: header (18 triplets at 68) and HV1 payload (80 at 122) ---- */
+		uint32_t hdr, hdr_ok;
 		{
-			uint32_t t = lane < 18 ? bits_at(ws.raw, 68 + 3 * lane, 3) : 0;
-			uint32_t ones = __popc(t);
-			uint32_t hdr = __ballot_sync(0xffffffffu, ones >= 2);
-			uint32_t bad = __ballot_sync(0xffffffffu, lane < 18 && (ones == 1 || ones == 2));
-			if (lane == 0) { ws.hdr = hdr & 0x3ffff; ws.hdr_ok = __popc(bad) < 18 / 4; }
-			int nbad = 0;
-			for (int r = 0; r < 3; r++) {
-				int i = r * 32 + lane;
-				uint32_t tt = i < 80 ? bits_at(ws.raw, 122 + 3 * i, 3) : 0;
-				uint32_t o = __popc(tt);
-				uint32_t v = __ballot_sync(0xffffffffu, o >= 2);
-				nbad += __popc(__ballot_sync(0xffffffffu, i < 80 && (o == 1 || o == 2)));
-				if (lane == 0) ws.hv1[r] = v;
-			}
-			if (lane == 0) { ws.hv1[3] = 0; ws.hv1_ok = nbad < 80 / 4; }
-		}
-		/* ---- FEC 2/3: all blocks, both alignments ---- */
-		for (int al = 0; al < 2; al++) {
-			uint32_t *dst = al ? ws.fec80 : ws.fec0;
-			const int start = al ? 202 : 122;
-			for (int w = lane; w <= FEC_WORDS; w += 32) dst[w] = 0;
-			__syncwarp();
-			int fail = 1 << 20;
-			for (int b0 = 0; b0 < FEC_BLOCKS; b0 += 32) {
-				int b = b0 + lane;
-				bool live = b < FEC_BLOCKS && start + 15 * b + 15 <= RAW_WORDS * 32;
-				uint32_t data = 0;
-				bool ok = true;
-				if (live) ok = fec23_block(bits_at(ws.raw, start + 15 * b, 15), s_col, &data);
-				uint32_t badmask = __ballot_sync(0xffffffffu, live && !ok);
-				if (badmask && fail == (1 << 20)) fail = b0 + __ffs(badmask) - 1;
-				if (live && ok) {
-					int pos = 10 * b;
-					atomicOr(&dst[pos >> 5], data << (pos & 31));
-					if ((pos & 31) > 22) atomicOr(&dst[(pos >> 5) + 1], data >> (32 - (pos & 31)));
-				}
-			}
-			if (lane == 0) { if (al) ws.fail80 = fail; else ws.fail0 = fail; }
+			uint32_t bit = 0, bad = 0;
+			if (lane < 18) btd_vote3(P, 68, lane, &bit, &bad);
+			hdr = __ballot_sync(FULL, bit) & 0x3ffffu;
+			hdr_ok = __popc(__ballot_sync(FULL, bad)) < 18 / 4;      /* unfec13: be < length / 4 (:563-567) */
+			if (lane == 0) { P.hdr = hdr; P.hdr_ok = (int)hdr_ok; }
 		}
 		__syncwarp();
-
-		dec_ctx d;
-		d.ws = &ws; d.wseq = s_wseq; d.phase = s_phase; d.crc = s_crc; d.whitened = in.whitened;
-		if (mode >= 2) {
-			/* single-function entry points of the classic API: type/UAP/clock supplied */
-			if (lane == 0) {
-				lane_state s;
-				memset(&s, 0, sizeof(s));
+		/* ---- which packet types are in play ---- */
+		btd_lane s;
+		uint32_t type_mask, hp = 0;
+		int header_ok = (int)hdr_ok;
+		if (OUT == OUT_ONE) {
+			btd_lane_init(s, (int)(in.clkn & 63));
+			if (mode == BTBB_B200_MODE_DECODE) {
+				header_ok = btd_decode_header(c, P, s, in.uap, &hp);
+				type_mask = header_ok ? 1u << s.type : 0u;
+			} else {
 				s.uap = in.uap; s.type = in.type & 15;
-				const int clock = (int)(in.clkn & 63);
-				int rv;
-				if (mode == BTBB_B200_MODE_PAYLOAD) rv = do_decode_payload(d, s, clock);
-				else if (mode == BTBB_B200_MODE_CRC_CHECK) rv = do_crc_check(d, s, clock);
-				else switch (mode - BTBB_B200_MODE_RAW) {
-				case 0: rv = dec_fhs(d, s, clock); break;
-				case 1: rv = dec_dm(d, s, clock); break;
-				case 2: rv = dec_dh(d, s, clock); break;
-				case 3: rv = dec_ev35(d, s, clock, 32); break;
-				case 4: rv = dec_ev4(d, s, clock); break;
-				case 5: rv = dec_ev35(d, s, clock, 182); break;
-				default: rv = dec_hv(d, s, clock); break;
-				}
-				emit_record(d, s, ws.hdr_ok, rv, 0, &out[p]);
-			}
-		} else if (mode == 0) {
-			if (lane == 0) {
-				lane_state s;
-				memset(&s, 0, sizeof(s));
-				s.uap = in.uap;
-				int ok = 0, rv = 0;
-				uint32_t hp = 0;
-				if (ws.hdr_ok) {
-					hp = ws.hdr ^ whiten_bits(s_wseq, s_phase, (int)in.clkn, 0, 18, in.whitened);
-					uint32_t d10 = hp & 0x3ff, hec = hp >> 10;
-					if (bt_uap_from_hec(d10, hec) == in.uap) {
-						s.lt_addr = hp & 7; s.type = (hp >> 3) & 15; s.flags = (hp >> 7) & 7; s.hec = hec;
-						ok = 1;
-					}
-				}
-				if (ok) rv = do_decode_payload(d, s, (int)(in.clkn & 63));
-				emit_record(d, s, ok, rv, hp, &out[p]);
+				type_mask = 1u << s.type;
 			}
 		} else {
-			for (int clock = lane; clock < 64; clock += 32) {
-				lane_state s;
-				memset(&s, 0, sizeof(s));
-				int ok = ws.hdr_ok;
-				if (ok) {
-					uint32_t hp = ws.hdr ^ whiten_bits(s_wseq, s_phase, clock, 0, 18, in.whitened);
-					s.uap = bt_uap_from_hec(hp & 0x3ff, hp >> 10);
-					s.type = (hp >> 3) & 15;
+			btd_lane t0, t1;
+			btd_lane_init(t0, lane); btd_lane_init(t1, lane + 32);
+			btd_try_clock(c, P, t0); btd_try_clock(c, P, t1);
+			type_mask = __reduce_or_sync(FULL, (1u << t0.type) | (1u << t1.type));
+		}
+		btd_needs nd;
+		btd_needs_for(type_mask, length, 0, &nd);
+		/* ---- the rest of the symbols that can matter ---- */
+		{
+			int w_end = (sh + nd.symbols + 31) / 32 + 1;
+			w_end = (w_end + 15) & ~15;
+			if (w_end > BTD_RAW_WORDS - 1) w_end = BTD_RAW_WORDS - 1;
+			ingest(P, base, sh, length, 16, w_end, lane);
+		}
+		__syncwarp();
+		/* ---- clock-independent work ---- */
+		if (nd.hv1) {
+			int nbad = 0;
+			for (int r = 0; r < 3; r++) {
+				const int i = r * 32 + lane;
+				uint32_t bit = 0, bad = 0;
+				if (i < 80) btd_vote3(P, 122, i, &bit, &bad);
+				const uint32_t v = __ballot_sync(FULL, bit);
+				nbad += __popc(__ballot_sync(FULL, bad));
+				if (lane == 0) P.hv1[r] = v;
+			}
+			if (lane == 0) { P.hv1[3] = 0; P.hv1_ok = nbad < 80 / 4; }
+		}
+		{
+			const int f0 = fec_blocks(P, P.fec0, 122, nd.nblk0, s_small->fec_col, lane);
+			const int f80 = nd.nblk80 ? fec_blocks(P, P.fec80, 202, nd.nblk80, s_small->fec_col, lane) : 1 << 20;
+			if (lane == 0) { P.fail0 = f0; P.fail80 = f80; }
+		}
+		__syncwarp();
+		build_dp(P, s_nib, BTD_SRC_RAW, nd.raw_bytes, P.dp_raw, lane);
+		build_dp(P, s_nib, BTD_SRC_FEC0, nd.fec0_bytes, P.dp_fec0, lane);
+		build_dp(P, s_nib, BTD_SRC_FEC80, nd.fec80_bytes, P.dp_fec80, lane);
+		build_dp(P, s_nib, BTD_SRC_FIRST8, nd.first8_bytes, P.dp_first8, lane);
+		__syncwarp();
+
+		if (OUT == OUT_ONE) {
+			/* every lane carries the same (clock, UAP, type): searches run on all 32 lanes */
+			if (mode == BTBB_B200_MODE_DECODE) {
+				if (header_ok) evaluate<true>(c, P, s, BTD_KIND_PAYLOAD, lane);
+			} else {
+				const int kind = mode == BTBB_B200_MODE_PAYLOAD ? BTD_KIND_PAYLOAD
+					       : mode == BTBB_B200_MODE_CRC_CHECK ? BTD_KIND_CRC_CHECK
+					       : BTD_KIND_RAW + (mode - BTBB_B200_MODE_RAW);
+				evaluate<true>(c, P, s, kind, lane);
+			}
+			const int nbits = btd_emit_bits(s, a.raw_payload);
+			const int q18 = btd_q(c, s.pay_clk, 18);
+			uint32_t *o = reinterpret_cast<uint32_t *>(&a.out[p]);
+			#pragma unroll
+			for (int i = 0; i < 3; i++) {
+				const int w = lane + 32 * i;
+				if (w < REC_WORDS) {
+					uint32_t v;
+					if (w < 7) v = btd_record_word(s, header_ok, hp, w);
+					else v = btd_pay_word(c, P, s.src, (q18 + 32 * (w - 7)) % 127, w - 7, nbits);
+					o[w] = v;
 				}
-				int rv = do_crc_check(d, s, clock);
-				if (tc16)      /* compact table for the UAP / CLK1-6 sieve (sieve.cu): UAP | class << 8 */
-					tc16[p * 64 + clock] = (uint16_t)(s.uap | ((rv == 0 ? 0 : rv == 1 ? 1 : rv == 2 ? 2 : rv == 10 ? 3 : 4) << 8));
-				else
-					emit_record(d, s, ok, rv, 0, &out[p * 64 + clock]);
+			}
+		} else {
+			#pragma unroll 1
+			for (int round = 0; round < 2; round++) {
+				btd_lane_init(s, lane + 32 * round);
+				btd_try_clock(c, P, s);
+				evaluate<false>(c, P, s, BTD_KIND_CRC_CHECK, lane);
+				if (OUT == OUT_TC16) {
+					a.tc16[p * 64 + s.clock] = (uint16_t)btd_tc16(s);
+				} else {
+					/* the previous bulk store has to be done reading the staging buffer */
+					if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+					__syncwarp();
+					uint32_t *rec = stage + lane * REC_WORDS;      /* 93 words apart: conflict-free */
+					#pragma unroll
+					for (int w = 0; w < 7; w++) rec[w] = btd_record_word(s, (int)hdr_ok, 0, w);
+					const int nbits = btd_emit_bits(s, a.raw_payload);
+					int q = btd_q(c, s.pay_clk, 18);
+					for (int j = 0; j < REC_WORDS - 7; j++) {
+						rec[7 + j] = btd_pay_word(c, P, s.src, q, j, nbits);
+						q += 32; if (q >= 127) q -= 127;
+					}
+					unsigned char *dst = reinterpret_cast<unsigned char *>(&a.out[p * 64 + 32 * round]);
+					if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+						__syncwarp();
+						if (lane == 0) {
+							const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+							asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+								     :: "l"(dst), "r"(src), "r"(STAGE_BYTES) : "memory");
+							asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+						}
+					} else {
+						__syncwarp();
+						uint32_t *o = reinterpret_cast<uint32_t *>(dst);
+						for (int w = lane; w < 32 * REC_WORDS; w += 32) o[w] = stage[w];
+					}
+					__syncwarp();
+				}
 			}
 		}
 		__syncwarp();
 	}
+	if (OUT == OUT_FULL64 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void header_present_kernel(const uint8_t *stream, int64_t stream_len,
@@ -499,30 +360,43 @@ __global__ void header_present_kernel(const uint8_t *stream, int64_t stream_len,
 	present[p] = be < 5;                               /* ID_THRESHOLD, bluetooth_packet.h:33 */
 }
 
-bool g_dec_tables_ready[16];
-
-int upload_dec_tables(int device)
+int ensure_dec_tables(btbb_b200_ctx *ctx)
 {
-	if (device >= 0 && device < 16 && g_dec_tables_ready[device]) return BTBB_B200_OK;
-	dec_tables t;
-	memset(&t, 0, sizeof(t));
-	uint8_t seq[127];
-	uint32_t s = bt_whiten_seed(0);
-	for (int i = 0; i < 127; i++) {
-		if ((s & 0x40) && (s & 0x3f) < 64) t.phase[s & 0x3f] = (uint8_t)i;
-		seq[i] = (uint8_t)bt_whiten_step(&s);
-	}
-	for (int i = 0; i < 13 * 32; i++)
-		t.wseq[i >> 5] |= (uint32_t)seq[i % 127] << (i & 31);
-	for (int b = 0; b < 256; b++) {
-		uint32_t reg = (uint32_t)b;
-		for (int i = 0; i < 8; i++) reg = (reg & 1) ? (reg >> 1) ^ 0x8408u : reg >> 1;
-		t.crc[b] = (uint16_t)reg;
-	}
-	for (int i = 0; i < 10; i++) t.fec_col[i] = (uint8_t)bt_fec23_parity(1u << i);
-	BT_CUDA_TRY(cudaMemcpyToSymbol(c_dec, &t, sizeof(t)));
-	if (device >= 0 && device < 16) g_dec_tables_ready[device] = true;
+	if (ctx->d_dec_tables) return BTBB_B200_OK;
+	const btd_tables *t = btd_host_tables();
+	void *d = NULL;
+	BT_CUDA_TRY(cudaMalloc(&d, sizeof(btd_tables)));
+	cudaError_t e = cudaMemcpy(d, t, sizeof(btd_tables), cudaMemcpyHostToDevice);
+	if (e != cudaSuccess) { cudaFree(d); return btbb_b200_cuda_fail(e, "cudaMemcpy(decode tables)"); }
+	ctx->d_dec_tables = d;
 	return BTBB_B200_OK;
+}
+
+template <int OUT, int WARPS>
+int launch(btbb_b200_ctx *ctx, const dec_args &a, int64_t n_max, cudaStream_t st)
+{
+	auto kern = decode_kernel<OUT, WARPS>;
+	constexpr int smem = smem_bytes<OUT, WARPS>();
+	static bool configured[16];
+	const int dev = ctx->device;
+	if (dev < 0 || dev >= 16 || !configured[dev]) {
+		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		if (dev >= 0 && dev < 16) configured[dev] = true;
+	}
+	int per_sm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+	int64_t blocks = (n_max + WARPS - 1) / WARPS;
+	const int64_t cap = (int64_t)ctx->sm_count * per_sm;
+	if (blocks > cap) blocks = cap;
+	kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(a);
+	BT_CUDA_TRY(cudaGetLastError());
+	return BTBB_B200_OK;
+}
+
+bool mode_ok(int mode)
+{
+	const int m = mode & ~BTBB_B200_MODE_FLAG_RAW_PAYLOAD;
+	return m >= 0 && (m <= 3 || (m >= 16 && m <= 22));
 }
 
 }  // namespace
@@ -531,18 +405,22 @@ extern "C" int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream,
 				    const btbb_b200_pkt_in *d_pkts, int64_t n, int mode,
 				    btbb_b200_decoded *d_out, void *cuda_stream)
 {
-	if (!ctx || n < 0 || (n > 0 && (!d_stream || !d_pkts || !d_out)) || stream_length < 0 || mode < 0 || (mode > 3 && (mode < 16 || mode > 22)))
+	if (!ctx || n < 0 || (n > 0 && (!d_stream || !d_pkts || !d_out)) || stream_length < 0 || !mode_ok(mode) ||
+	    (reinterpret_cast<uintptr_t>(d_out) & 3))
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "decode: bad arguments");
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
-	int rc = upload_dec_tables(ctx->device);
+	int rc = ensure_dec_tables(ctx);
 	if (rc) return rc;
 	if (n == 0) return BTBB_B200_OK;
-	int64_t blocks = (n + WARPS - 1) / WARPS;
-	int64_t cap = (int64_t)ctx->sm_count * 16;
-	if (blocks > cap) blocks = cap;
-	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, (cudaStream_t)cuda_stream>>>(d_stream, stream_length, d_pkts, n, mode, d_out, NULL, NULL, NULL);
-	BT_CUDA_TRY(cudaGetLastError());
-	return BTBB_B200_OK;
+	dec_args a;
+	memset(&a, 0, sizeof(a));
+	a.stream = d_stream; a.stream_len = stream_length; a.pkts = d_pkts; a.n = n;
+	a.raw_payload = (mode & BTBB_B200_MODE_FLAG_RAW_PAYLOAD) != 0;
+	a.mode = mode & ~BTBB_B200_MODE_FLAG_RAW_PAYLOAD;
+	a.out = d_out; a.tables = static_cast<const btd_tables *>(ctx->d_dec_tables);
+	if (a.mode == BTBB_B200_MODE_TRY_CLOCKS)
+		return launch<OUT_FULL64, 12>(ctx, a, n, (cudaStream_t)cuda_stream);
+	return launch<OUT_ONE, 8>(ctx, a, n, (cudaStream_t)cuda_stream);
 }
 
 /* try_clock + crc_check for CLK1-6 = 0..63 (bluetooth_piconet.c:675-689) of the packets listed in
@@ -553,16 +431,24 @@ int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t s
 			  const btbb_b200_pkt_in *d_pkts, const int64_t *d_idx, const unsigned long long *d_n,
 			  int64_t n_max, uint16_t *d_tc, cudaStream_t st)
 {
-	int rc = upload_dec_tables(ctx->device);
+	int rc = ensure_dec_tables(ctx);
 	if (rc) return rc;
 	if (n_max == 0) return BTBB_B200_OK;
-	int64_t blocks = (n_max + WARPS - 1) / WARPS;
-	int64_t cap = (int64_t)ctx->sm_count * 16;
-	if (blocks > cap) blocks = cap;
-	decode_kernel<<<(unsigned)blocks, WARPS * 32, 0, st>>>(d_stream, stream_length, d_pkts, n_max, BTBB_B200_MODE_TRY_CLOCKS,
-							      NULL, d_tc, d_idx, d_n);
-	BT_CUDA_TRY(cudaGetLastError());
-	return BTBB_B200_OK;
+	dec_args a;
+	memset(&a, 0, sizeof(a));
+	a.stream = d_stream; a.stream_len = stream_length; a.pkts = d_pkts; a.n = n_max;
+	a.mode = BTBB_B200_MODE_TRY_CLOCKS; a.tc16 = d_tc; a.idx = d_idx; a.n_dev = d_n;
+	a.tables = static_cast<const btd_tables *>(ctx->d_dec_tables);
+	return launch<OUT_TC16, 8>(ctx, a, n_max, st);
+}
+
+extern "C" int btbb_b200_try_clocks_compact_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
+						const btbb_b200_pkt_in *d_pkts, int64_t n, uint16_t *d_tc, void *cuda_stream)
+{
+	if (!ctx || n < 0 || (n > 0 && (!d_stream || !d_pkts || !d_tc)) || stream_length < 0)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "try_clocks_compact: bad arguments");
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	return bt_try_clocks_compact(ctx, d_stream, stream_length, d_pkts, NULL, NULL, n, d_tc, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int btbb_b200_header_present_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t stream_length,
@@ -578,29 +464,50 @@ extern "C" int btbb_b200_header_present_dev(btbb_b200_ctx *ctx, const uint8_t *d
 	return BTBB_B200_OK;
 }
 
+/* grow-only device scratch of the host-buffer entry points (no cudaMalloc per call) */
+static int ensure_scratch(btbb_b200_ctx *ctx, int which, size_t bytes, void **out)
+{
+	if (bytes > ctx->scratch_cap[which]) {
+		if (ctx->d_scratch[which]) cudaFree(ctx->d_scratch[which]);
+		ctx->d_scratch[which] = NULL; ctx->scratch_cap[which] = 0;
+		size_t cap = bytes < 65536 ? 65536 : bytes + bytes / 4;
+		BT_CUDA_TRY(cudaMalloc(&ctx->d_scratch[which], cap));
+		ctx->scratch_cap[which] = cap;
+	}
+	*out = ctx->d_scratch[which];
+	return BTBB_B200_OK;
+}
+
 extern "C" int btbb_b200_decode_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
 				     const btbb_b200_pkt_in *pkts, int64_t n, int mode, btbb_b200_decoded *out)
 {
-	if (!ctx || n < 0 || (n > 0 && (!stream || !pkts || !out)) || stream_length < 0 || mode < 0 || (mode > 3 && (mode < 16 || mode > 22)))
+	if (!ctx || n < 0 || (n > 0 && (!stream || !pkts || !out)) || stream_length < 0 || !mode_ok(mode))
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "decode_host: bad arguments");
 	if (n == 0) return BTBB_B200_OK;
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
-	uint8_t *d_s = NULL; btbb_b200_pkt_in *d_p = NULL; btbb_b200_decoded *d_o = NULL;
-	int64_t nout = mode == BTBB_B200_MODE_TRY_CLOCKS ? n * 64 : n;
-	int rc = BTBB_B200_OK;
+	std::lock_guard<std::mutex> guard(*ctx->host_lock);
+	void *d_s = NULL, *d_p = NULL, *d_o = NULL;
+	const int64_t nout = (mode & ~BTBB_B200_MODE_FLAG_RAW_PAYLOAD) == BTBB_B200_MODE_TRY_CLOCKS ? n * 64 : n;
+	int rc = ensure_scratch(ctx, 0, (size_t)stream_length + 64, &d_s);
+	if (!rc) rc = ensure_scratch(ctx, 1, (size_t)n * sizeof(btbb_b200_pkt_in), &d_p);
+	if (!rc) rc = ensure_scratch(ctx, 2, (size_t)nout * sizeof(btbb_b200_decoded), &d_o);
+	if (rc) return rc;
 	cudaError_t e;
-	if ((e = cudaMalloc(&d_s, (size_t)stream_length + 1)) != cudaSuccess ||
-	    (e = cudaMalloc(&d_p, (size_t)n * sizeof(*d_p))) != cudaSuccess ||
-	    (e = cudaMalloc(&d_o, (size_t)nout * sizeof(*d_o))) != cudaSuccess)
-		rc = btbb_b200_cuda_fail(e, "cudaMalloc(decode_host)");
-	if (!rc && ((e = cudaMemcpy(d_s, stream, (size_t)stream_length, cudaMemcpyHostToDevice)) != cudaSuccess ||
-		    (e = cudaMemcpy(d_p, pkts, (size_t)n * sizeof(*d_p), cudaMemcpyHostToDevice)) != cudaSuccess))
-		rc = btbb_b200_cuda_fail(e, "cudaMemcpy(decode_host H2D)");
-	if (!rc) rc = btbb_b200_decode_dev(ctx, d_s, stream_length, d_p, n, mode, d_o, NULL);
-	if (!rc && (e = cudaMemcpy(out, d_o, (size_t)nout * sizeof(*d_o), cudaMemcpyDeviceToHost)) != cudaSuccess)
-		rc = btbb_b200_cuda_fail(e, "cudaMemcpy(decode_host D2H)");
-	if (d_s) cudaFree(d_s);
-	if (d_p) cudaFree(d_p);
-	if (d_o) cudaFree(d_o);
-	return rc;
+	if ((e = cudaMemcpy(d_s, stream, (size_t)stream_length, cudaMemcpyHostToDevice)) != cudaSuccess ||
+	    (e = cudaMemcpy(d_p, pkts, (size_t)n * sizeof(btbb_b200_pkt_in), cudaMemcpyHostToDevice)) != cudaSuccess)
+		return btbb_b200_cuda_fail(e, "cudaMemcpy(decode_host H2D)");
+	rc = btbb_b200_decode_dev(ctx, static_cast<const uint8_t *>(d_s), stream_length, static_cast<const btbb_b200_pkt_in *>(d_p),
+				  n, mode, static_cast<btbb_b200_decoded *>(d_o), NULL);
+	if (rc) return rc;
+	if ((e = cudaMemcpy(out, d_o, (size_t)nout * sizeof(btbb_b200_decoded), cudaMemcpyDeviceToHost)) != cudaSuccess)
+		return btbb_b200_cuda_fail(e, "cudaMemcpy(decode_host D2H)");
+	return BTBB_B200_OK;
+}
+
+extern "C" int btbb_b200_decode_smallcall(const char *symbols, int length, uint32_t clkn, uint8_t uap,
+					  int whitened, uint8_t type, int mode, btbb_b200_decoded *out)
+{
+	if (!symbols || !out || !mode_ok(mode))
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "decode_smallcall: bad arguments");
+	return bt_decode_one_cpu(symbols, length, clkn, uap, whitened, type, mode, out);
 }

@@ -304,14 +304,14 @@ constexpr int SORT_CHUNK = 512;    /* records per warp */
 constexpr int SORT_BITS = 9;       /* digit width: offsets below 2^36 sort in 4 passes */
 constexpr int SORT_BINS = 1 << SORT_BITS;
 
-__global__ void sort_hist_kernel(const btbb_b200_hit *in, int64_t n, int shift, uint32_t *hist, int nblk)
+__global__ void sort_hist_kernel(const btbb_b200_hit *in, int64_t n, int shift, uint32_t *hist, int nblk, int64_t key_bias)
 {
 	__shared__ uint32_t h[SORT_BINS];
 	for (int i = threadIdx.x; i < SORT_BINS; i += 32) h[i] = 0;
 	__syncwarp();
 	int64_t b0 = (int64_t)blockIdx.x * SORT_CHUNK, b1 = b0 + SORT_CHUNK < n ? b0 + SORT_CHUNK : n;
 	for (int64_t i = b0 + threadIdx.x; i < b1; i += 32)
-		atomicAdd(&h[(uint32_t)((uint64_t)in[i].offset >> shift) & (SORT_BINS - 1)], 1u);
+		atomicAdd(&h[(uint32_t)((uint64_t)(in[i].offset - key_bias) >> shift) & (SORT_BINS - 1)], 1u);
 	__syncwarp();
 	for (int i = threadIdx.x; i < SORT_BINS; i += 32) hist[(int64_t)i * nblk + blockIdx.x] = h[i];
 }
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) sort_rowscan_kernel(uint32_t *hist, int n
 }
 
 __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out, int64_t n, int shift,
-				    const uint32_t *hist, int nblk, const uint32_t *tot)
+				    const uint32_t *hist, int nblk, const uint32_t *tot, int64_t key_bias)
 {
 	__shared__ uint32_t cur[SORT_BINS];
 	const int lane = threadIdx.x;
@@ -372,7 +372,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 		bool live = i < b1;
 		btbb_b200_hit rec;
 		uint32_t dig = 0;
-		if (live) { rec = in[i]; dig = (uint32_t)((uint64_t)rec.offset >> shift) & (SORT_BINS - 1); }
+		if (live) { rec = in[i]; dig = (uint32_t)((uint64_t)(rec.offset - key_bias) >> shift) & (SORT_BINS - 1); }
 		unsigned act = __ballot_sync(0xffffffffu, live);
 		if (live) {
 			unsigned peers = __match_any_sync(act, dig);
@@ -691,18 +691,20 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 }
 
 /* LSD radix sort by offset; `a` holds `have` records, `b` is scratch.  *result = the buffer
- * that ends up sorted (a when the number of passes is even, else b). */
+ * that ends up sorted (a when the number of passes is even, else b).  The digits are taken from
+ * offset - key_bias, which lies in [0, span) for the span the pass count was derived from
+ * (records carry offset + bias, btbb_b200_set_offset_bias). */
 int bt_sort_hits(btbb_b200_ctx *ctx, btbb_b200_hit *a, btbb_b200_hit *b, int64_t have,
-		 int passes, cudaStream_t st, btbb_b200_hit **result)
+		 int passes, int64_t key_bias, cudaStream_t st, btbb_b200_hit **result)
 {
 	btbb_b200_hit *src = a, *dst = b;
 	if (have > 0) {
 		int nblk = (int)((have + SORT_CHUNK - 1) / SORT_CHUNK);
 		for (int p = 0; p < passes; p++) {
-			sort_hist_kernel<<<nblk, 32, 0, st>>>(src, have, SORT_BITS * p, ctx->d_sort_hist, nblk);
+			sort_hist_kernel<<<nblk, 32, 0, st>>>(src, have, SORT_BITS * p, ctx->d_sort_hist, nblk, key_bias);
 			uint32_t *tot = ctx->d_sort_hist + (int64_t)nblk * SORT_BINS;
 			sort_rowscan_kernel<<<SORT_BINS / 8, 256, 0, st>>>(ctx->d_sort_hist, nblk, tot);
-			sort_scatter_kernel<<<nblk, 32, 0, st>>>(src, dst, have, SORT_BITS * p, ctx->d_sort_hist, nblk, tot);
+			sort_scatter_kernel<<<nblk, 32, 0, st>>>(src, dst, have, SORT_BITS * p, ctx->d_sort_hist, nblk, tot, key_bias);
 			btbb_b200_hit *t = src; src = dst; dst = t;
 		}
 		BT_CUDA_TRY(cudaGetLastError());
@@ -908,6 +910,7 @@ int bt_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: a call is already pending on this context");
 	pd.d_stream = d_stream; pd.packed = packed; pd.search_length = search_length; pd.lap = lap;
 	pd.max_ac_errors = max_ac_errors; pd.d_hits = d_hits; pd.max_hits = max_hits; pd.st = st;
+	pd.bias = ctx->hit_bias;
 	pd.mode = BT_PENDING_GENERIC;
 	if (search_length == 0) { pd.mode = BT_PENDING_EMPTY; return BTBB_B200_OK; }
 	int rc = bt_ensure_tmp(ctx, max_hits > 0 ? max_hits : 1);
@@ -921,7 +924,7 @@ int bt_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed
 	bt_slab_req req;
 	cudaError_t e = cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(unsigned long long), st);
 	if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "cudaMemsetAsync(find_ac counters)"); }
-	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, ctx->hit_bias, st, &req, packed);
+	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, pd.bias, st, &req, packed);
 	if (rc) { pd.mode = BT_PENDING_NONE; return rc; }
 	if (req.used) {
 		const int nw = req.nw;
@@ -974,7 +977,7 @@ int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
 			*n_hits = (int64_t)total;
 			int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 			btbb_b200_hit *res = NULL;
-			rc = bt_sort_hits(ctx, ctx->d_tmp, d_hits, have, bt_sort_passes(search_length), st, &res);
+			rc = bt_sort_hits(ctx, ctx->d_tmp, d_hits, have, bt_sort_passes(search_length), pd.bias, st, &res);
 			if (rc) return rc;
 			if (res != d_hits && have > 0)
 				BT_CUDA_TRY(cudaMemcpyAsync(d_hits, res, (size_t)have * sizeof(btbb_b200_hit), cudaMemcpyDeviceToDevice, st));
@@ -989,7 +992,7 @@ int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
 	btbb_b200_hit *first = (passes & 1) ? ctx->d_tmp : d_hits;
 	btbb_b200_hit *other = (passes & 1) ? d_hits : ctx->d_tmp;
 	BT_CUDA_TRY(cudaMemsetAsync(ctx->d_count, 0, sizeof(unsigned long long), st));
-	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, ctx->hit_bias, st, NULL, packed);
+	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, first, max_hits, ctx->d_count, pd.bias, st, NULL, packed);
 	if (rc) return rc;
 	BT_CUDA_TRY(cudaMemcpyAsync(&total, ctx->d_count, sizeof(total), cudaMemcpyDeviceToHost, st));
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
@@ -998,7 +1001,7 @@ int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
 	*n_hits = (int64_t)total;
 	int64_t have = (int64_t)total < max_hits ? (int64_t)total : max_hits;
 	btbb_b200_hit *res = NULL;
-	rc = bt_sort_hits(ctx, first, other, have, passes, st, &res);
+	rc = bt_sort_hits(ctx, first, other, have, passes, pd.bias, st, &res);
 	if (rc) return rc;
 	BT_CUDA_TRY(cudaStreamSynchronize(st));
 	if ((int64_t)total > max_hits)

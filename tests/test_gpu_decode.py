@@ -107,3 +107,70 @@ def test_header_present(gpu_ctx2, orc, product_lib):
     torch.cuda.synchronize()
     want = [orc.orc_header_present(s[p.offset:].ctypes.data, int(pk["length"][i])) for i, p in enumerate(pl)]
     assert d_r.cpu().numpy().tolist() == want and 0 < sum(want) < len(want)
+
+
+def test_crafted_crc_success_paths_on_gpu(gpu_ctx2, orc):
+    """EV4 / FHS (own and other clock) / DV / EV3 / EV5 CRC closures, the raw-payload flag and an
+    odd output alignment, all through the kernels; every record against the oracle."""
+    rng = np.random.default_rng(2024)
+    cases = list(util.crafted_packets(orc, rng, 260))
+    cases += [("ev35", sym, 3125, clk, uap) for sym, clk, uap in util.ev35_hunt(orc, rng, 1500)]
+    s = np.concatenate([c[1] for c in cases])
+    pk = np.zeros(len(cases), dtype=B.PKTIN_DTYPE)
+    for i, (_, _, n, clk, uap) in enumerate(cases):
+        pk[i]["offset"], pk[i]["length"], pk[i]["clkn"], pk[i]["uap"], pk[i]["whitened"] = i * 3125, n, clk, uap, 1
+    got = gpu_ctx2.decode_host(s, pk, mode=0)
+    raw = gpu_ctx2.decode_host(s, pk, mode=B.MODE_FLAG_RAW_PAYLOAD)
+    closures = 0
+    for i, (_, sym, n, clk, uap) in enumerate(cases):
+        want = util.decode_one(orc, "orc", sym, 0, n, clk, uap)
+        assert got[i].tobytes() == want.tobytes(), (i, got[i], want)
+        assert raw[i].tobytes() == util.decode_one_raw(orc, "orc", sym, 0, n, clk, uap).tobytes(), (i, "raw")
+        closures += int(want["rv"] >= 10)
+    assert closures > 150
+    sub = pk[:128]
+    tc = gpu_ctx2.decode_host(s, sub, mode=1).reshape(len(sub), 64)
+    tcr = gpu_ctx2.decode_host(s, sub, mode=1 | B.MODE_FLAG_RAW_PAYLOAD).reshape(len(sub), 64)
+    for i in range(len(sub)):
+        for c in range(64):
+            want = util.try_clock_one(orc, "orc", cases[i][1], 0, cases[i][2], c)
+            assert tc[i, c].tobytes() == want.tobytes(), (i, c, tc[i, c], want)
+        # raw flag: same fields, payload bytes also where rv < 2
+        assert (tcr[i]["rv"] == tc[i]["rv"]).all() and (tcr[i]["payload_length"] == tc[i]["payload_length"]).all()
+        ok = tc[i]["rv"] >= 2
+        assert (tcr[i]["payload"][ok] == tc[i]["payload"][ok]).all()
+
+
+def test_device_entry_points_match_smallcall_and_compact(gpu_ctx2, product_lib):
+    """btbb_b200_decode_dev with a misaligned stream pointer and a 4-byte (not 16-byte) aligned output
+    (the bulk-store path needs 16), the compact try-clocks table, and the host small-call path: all
+    the same records."""
+    import ctypes as C
+    import torch
+    cfg = B.synth_cfg(900_000, stride=3300, ber=0.004, seed=77, mix=tuple(B.KIND))
+    s = B.synth_host(cfg)
+    pl = util.planted_list(cfg)[:200]
+    pk = pkts_for(pl, s)
+    ref1 = gpu_ctx2.decode_host(s, pk, mode=1).reshape(len(pl), 64)
+    ref0 = gpu_ctx2.decode_host(s, pk, mode=0)
+    for i in range(0, len(pl), 9):
+        sym = np.ascontiguousarray(s[pl[i].offset:pl[i].offset + int(pk[i]["length"])])
+        assert B.decode_smallcall(sym, len(sym), int(pk[i]["clkn"]), int(pk[i]["uap"]))[0].tobytes() == ref0[i].tobytes()
+        assert B.decode_smallcall(sym, len(sym), mode=1).tobytes() == ref1[i].tobytes()
+    d_raw = torch.zeros(len(s) + 64 + 5, dtype=torch.uint8, device="cuda")
+    d_raw[5:5 + len(s)] = torch.from_numpy(s).cuda()
+    d_p = torch.from_numpy(pk.view(np.uint8)).cuda()
+    d_o = torch.zeros(len(pl) * 64 * 372 + 16, dtype=torch.uint8, device="cuda")
+    for shift in (0, 4):
+        B.check(product_lib.btbb_b200_decode_dev(gpu_ctx2.h, d_raw.data_ptr() + 5, len(s), d_p.data_ptr(), len(pl), 1,
+                                                 d_o.data_ptr() + shift, 0))
+        torch.cuda.synchronize()
+        got = d_o[shift:shift + len(pl) * 64 * 372].cpu().numpy().view(B.DECODED_DTYPE).reshape(len(pl), 64)
+        assert got.tobytes() == ref1.tobytes(), shift
+    d_tc = torch.zeros(len(pl) * 64, dtype=torch.int16, device="cuda")
+    B.check(product_lib.btbb_b200_try_clocks_compact_dev(gpu_ctx2.h, d_raw.data_ptr() + 5, len(s), d_p.data_ptr(), len(pl),
+                                                         d_tc.data_ptr(), 0))
+    torch.cuda.synchronize()
+    tc = d_tc.cpu().numpy().view(np.uint16).reshape(len(pl), 64)
+    cls = np.select([ref1["rv"] == 0, ref1["rv"] == 1, ref1["rv"] == 2, ref1["rv"] == 10], [0, 1, 2, 3], 4)
+    assert ((tc & 0xff) == ref1["uap"]).all() and ((tc >> 8) == cls).all()

@@ -194,3 +194,81 @@ def sieve_run(L, prefix, stream, pkts, gs, states=None):
                                       gs.ctypes.data, len(st), st.ctypes.data, rv.ctypes.data)
     return st, rv
 
+
+
+# ---- crafted packets: the CRC-success paths of every search (EV3 / EV4 / EV5 lengths, fhs clocks, DV) ----
+def _bits(v, n):
+    return [(v >> i) & 1 for i in range(n)]
+
+
+def _whiten(orc, bits, clk, skip):
+    return [int(b) ^ orc.orc_whiten_bit(clk, skip + i) for i, b in enumerate(bits)]
+
+
+def _fec23(orc, bits):
+    out = []
+    bits = list(bits) + [0] * (-len(bits) % 10)
+    for b in range(0, len(bits), 10):
+        d = int(sum(int(bits[b + i]) << i for i in range(10)))
+        out += _bits(orc.orc_fec23(d), 15)
+    return out
+
+
+def _with_crc(orc, body_bytes, uap):
+    bits = [b for byte in body_bytes for b in _bits(int(byte), 8)]
+    arr = np.array(bits, dtype=np.uint8)
+    crc = orc.orc_crc16(arr.ctypes.data, len(bits), uap)
+    return bits + _bits(crc, 16)
+
+
+def _craft(orc, rng, ptype, clk, uap, payload_symbols):
+    sym = rng.integers(0, 2, 3125, dtype=np.uint8)
+    d10 = int(rng.integers(0, 8)) | (ptype << 3) | (int(rng.integers(0, 8)) << 7)
+    hdr = _bits(d10 | (orc.orc_hec(d10, uap) << 10), 18)
+    sym[68:122] = np.repeat(np.array(_whiten(orc, hdr, clk, 0), dtype=np.uint8), 3)
+    n = min(len(payload_symbols), 3125 - 122)
+    sym[122:122 + n] = payload_symbols[:n]
+    return sym
+
+
+def crafted_packets(orc, rng, count):
+    """Packets whose payload CRC closes on the paths a random capture hardly ever reaches: EV4 at a
+    chosen length (optionally in front of an uncorrectable block / a short capture), FHS whitened
+    with its own clock or with one of 32..63, DV, EV3 / EV5.  Yields (kind, symbols, length, clk, uap)."""
+    for i in range(count):
+        clk, uap = int(rng.integers(0, 64)), int(rng.integers(0, 256))
+        kind = i % 4
+        if kind == 0:
+            L = int(rng.integers(3, 120))
+            pay = _with_crc(orc, rng.integers(0, 256, L - 2), uap)
+            pay += list(rng.integers(0, 2, 10 * 98 - len(pay) if 10 * 98 > len(pay) else 0))
+            sym = _craft(orc, rng, 12, clk, uap, _fec23(orc, _whiten(orc, pay, clk, 18)))
+            if i % 8 == 4:
+                b = int(rng.integers(0, 90))
+                sym[122 + 15 * b:122 + 15 * b + 3] ^= 1
+            n = int(rng.choice([3125, 122 + 15 * int(rng.integers(1, 98)) + int(rng.integers(0, 15))]))
+        elif kind == 1:
+            pay = _with_crc(orc, rng.integers(0, 256, 18), uap)
+            clk2 = clk if i % 8 == 1 else int(rng.integers(32, 64))
+            sym = _craft(orc, rng, 2, clk, uap, _fec23(orc, _whiten(orc, pay, clk2, 18)))
+            if i % 16 == 5:
+                sym[122 + int(rng.integers(0, 240))] ^= 1
+            n = 3125 if i % 5 else 362
+        elif kind == 2:
+            nb = int(rng.integers(0, 10))
+            hdr = int(rng.integers(0, 8)) | (nb << 3)
+            pay = _with_crc(orc, [hdr] + list(rng.integers(0, 256, nb)), uap)
+            s = list(rng.integers(0, 2, 80)) + _fec23(orc, _whiten(orc, pay, clk, 18))
+            sym = _craft(orc, rng, 8, clk, uap, s)
+            n = 3125 if i % 3 else 202 + 15 * ((8 * (nb + 3) + 9) // 10) + int(rng.integers(0, 40))
+        else:
+            sym = _craft(orc, rng, 7 if i % 8 == 3 else 13, clk, uap, rng.integers(0, 2, 3000, dtype=np.uint8))
+            n = int(rng.choice([3125, 1000, 400, 200]))
+        yield ("ev4", "fhs_own" if i % 8 == 1 else "fhs_other", "dv", "ev35")[kind] if kind != 1 else ("fhs_own" if i % 8 == 1 else "fhs_other"), sym, n, clk, uap
+
+
+def ev35_hunt(orc, rng, count):
+    """EV3 / EV5 packets on random symbols (a CRC closure is luck: about one in 400 for EV5)."""
+    for i in range(count):
+        clk, uap = int(rng.integers(0, 64)), int(rng.integers(0, 256))
+        yield _craft(orc, rng, 13 if i % 4 else 7, clk, uap, rng.integers(0, 2, 3000, dtype=np.uint8)), clk, uap

@@ -30,7 +30,17 @@ ctx = B.Context(0, 2)
 st = torch.cuda.current_stream().cuda_stream
 
 
-def chain(mode):
+# ground truth per 4096-symbol slot (clock / UAP the planted packet was whitened / HEC'ed with)
+n_slots = a.blocks * CH
+truth = np.zeros((n_slots, 2), dtype=np.int32)
+for sl in range(n_slots):
+    p = B.planted(cfg, sl)
+    truth[sl] = (p.clk6, p.uap)
+d_truth = torch.from_numpy(truth).cuda()
+out_buf = torch.empty((cap * 64, 372), dtype=torch.uint8, device="cuda") if cap * 64 * 372 < 40e9 else None
+
+
+def chain(mode, true_clock=False):
     cnt, rc = ctx.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, k=2, stream=st)
     off = d_hits[:cnt].view(torch.int64)[:, 0]
     pk = torch.zeros((cnt, 24), dtype=torch.uint8, device="cuda")
@@ -38,24 +48,53 @@ def chain(mode):
     length = torch.clamp((off // BLK + 1) * BLK - off, max=3125).to(torch.int32)   # symbols left in the channel block
     pk.view(torch.int32)[:, 2] = length
     pk[:, 17] = 1                                                                  # whitened
-    out = torch.empty((cnt * (64 if mode == 1 else 1), 372), dtype=torch.uint8, device="cuda")
+    if true_clock:
+        t = d_truth[torch.clamp(off // BLK, max=n_slots - 1)]
+        pk.view(torch.int32)[:, 3] = t[:, 0]
+        pk[:, 16] = t[:, 1].to(torch.uint8)
+    out = out_buf[: cnt * (64 if mode == 1 else 1)]
     B.check(lib.btbb_b200_decode_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, mode, out.data_ptr(), st))
     return cnt, pk, out
 
 
+def kernel_only(mode, pk, cnt, out, iters=10):
+    """the decode kernel alone on a fixed packet list (CUDA events on its stream)"""
+    for _ in range(2):
+        B.check(lib.btbb_b200_decode_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, mode, out.data_ptr(), st))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        B.check(lib.btbb_b200_decode_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, mode, out.data_ptr(), st))
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 res = {"workload": f"{a.blocks} blocks x 79 channels x 4096 symbols, one packet per channel block, BER 0.1%",
        "symbols": n}
-for mode, name in ((1, "find_ac + 64-clock try_clock/crc_check sweep"), (0, "find_ac + decode (clock 0, UAP 0: header reject path)")):
+for mode, tc, name in ((1, False, "find_ac + 64-clock try_clock/crc_check sweep"),
+                       (0, True, "find_ac + decode with the true clock / UAP (header + payload + CRC)"),
+                       (0, False, "find_ac + decode (clock 0, UAP 0: header reject path)")):
     for _ in range(2):
-        cnt, pk, out = chain(mode)
+        cnt, pk, out = chain(mode, tc)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.iters):
-        cnt, pk, out = chain(mode)
+        cnt, pk, out = chain(mode, tc)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
-    res[name] = {"ms": ms, "packets": int(cnt), "packets_per_s": cnt / (ms / 1e3), "gbit_s": n / (ms / 1e3) / 1e9}
+    kms = kernel_only(mode, pk, cnt, out)
+    pkh = pk.cpu().numpy().reshape(-1).view(B.PKTIN_DTYPE)
+    rec = out[:cnt].cpu().numpy().reshape(-1).view(B.DECODED_DTYPE) if mode == 0 else None
+    sym_bytes = int(np.minimum(pkh["length"], 3125).sum())
+    out_bytes = cnt * 372 * (64 if mode == 1 else 1)
+    res[name] = {"ms": ms, "packets": int(cnt), "packets_per_s": cnt / (ms / 1e3), "gbit_s": n / (ms / 1e3) / 1e9,
+                 "decode_kernel_ms": kms, "decode_kernel_packets_per_s": cnt / (kms / 1e3),
+                 "decode_kernel_GBps_symbols_plus_records": (sym_bytes + out_bytes) / (kms / 1e3) / 1e9,
+                 "symbol_bytes": sym_bytes, "record_bytes": out_bytes}
+    if rec is not None:
+        res[name]["rv_histogram"] = {str(int(k)): int(v) for k, v in zip(*np.unique(rec["rv"], return_counts=True))}
 # ---- UAP / CLK1-6 discovery (SURVEY.md 8(f) row 1) on a piconet-coherent capture: find_ac -> group hits by LAP
 # -> btbb_b200_uap_sieve_dev.  CLKN of a packet = its 4096-symbol slot index, channel = slot % 79. ----
 cfg2 = B.synth_cfg(n + 63, stride=BLK, ber=0.001, mix=("DM1", "DM3", "DH1", "FHS", "HV1"), piconets=True)
