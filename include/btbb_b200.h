@@ -126,6 +126,12 @@ int btbb_b200_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits);
  * straight from the kernels. */
 int btbb_b200_set_offset_bias(btbb_b200_ctx *ctx, int64_t bias);
 
+/* Measurement hook (bench.py's roofline): with profiling on, every scan records CUDA events right
+ * before and after its bulk kernel on the scan's own stream; after the scan has been waited for,
+ * btbb_b200_last_scan_kernel_ms returns that kernel's duration.  Off by default. */
+int btbb_b200_set_profiling(btbb_b200_ctx *ctx, int on);
+int btbb_b200_last_scan_kernel_ms(btbb_b200_ctx *ctx, float *ms);
+
 /*
  * btbb_b200_find_ac_dev for a stream that is already PACKED, 32 symbols per word: symbol i of
  * the stream is bit (i & 31) of d_words[i >> 5] -- the reference's own bit order when it packs
@@ -245,6 +251,49 @@ int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t str
 			     const btbb_b200_pkt_in *pkts, int64_t n_pkts,
 			     const int64_t *group_start, int64_t n_groups,
 			     btbb_b200_sieve *states, int8_t *rv);
+
+/*
+ * ---- multi-GPU: one process per GPU, contiguous shards, all-gather of hit records ----
+ * Rank r of `world` scans positions [first_position, first_position + search_length) of the global
+ * stream from a device buffer holding that range plus 63 more symbols (the north star fixes the
+ * seam overlap at 72); the kernels report GLOBAL offsets.  Ranges partition the positions, so the
+ * rank-order concatenation of the per-rank sorted lists is the sorted list of the whole stream.
+ * The records travel over NVLink peer memory (CUDA IPC mapped gather buffers, plain device-to-device
+ * copies on a copy stream, so the exchange of one scan runs underneath the next scan) or, with
+ * BTBB_B200_SHARD_NCCL_ONLY or where peer mapping fails, as an NCCL allgatherv (one all-gather of
+ * the counts + one group of exact-size broadcasts).  NCCL (libnccl.so.2) is loaded on first use.
+ *
+ *   rank 0:      btbb_b200_shard_unique_id(id); hand the 128 bytes to every rank (any transport)
+ *   every rank:  btbb_b200_shard_init(ctx, id, rank, world, slot_records, flags)
+ *   per scan:    btbb_b200_find_ac_sharded_begin(...)   enqueue the scan of this rank's shard
+ *                btbb_b200_find_ac_sharded_end(...)     wait for it, start pushing its records
+ *                btbb_b200_find_ac_sharded_next(...)    = _end of this scan + _begin of the next one,
+ *                                                       the push overlapping that next scan
+ *   finally:     btbb_b200_find_ac_sharded_gather(...)  every rank's records of the latest scan
+ * btbb_b200_find_ac_sharded_dev is begin + end + gather + concatenation into one buffer.
+ * slot_records bounds the hits ONE rank may report per scan (BTBB_B200_EOVERFLOW beyond).
+ */
+#define BTBB_B200_SHARD_ID_BYTES 128
+#define BTBB_B200_SHARD_NCCL_ONLY 1
+int btbb_b200_shard_unique_id(void *id);
+int btbb_b200_shard_init(btbb_b200_ctx *ctx, const void *id, int rank, int world, int64_t slot_records, int flags);
+int btbb_b200_shard_info(const btbb_b200_ctx *ctx, int *rank, int *world, int *peer_memory);
+int btbb_b200_shard_destroy(btbb_b200_ctx *ctx);
+int btbb_b200_find_ac_sharded_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+				    int64_t first_position, uint32_t lap, int max_ac_errors, void *cuda_stream);
+int btbb_b200_find_ac_sharded_end(btbb_b200_ctx *ctx, int64_t *n_local);
+/* _end of the pending scan + _begin of the next, ordered so that the GPU never idles: wait for
+ * scan i, enqueue scan i + 1, then push scan i's records underneath it; *n_prev = scan i's hits */
+int btbb_b200_find_ac_sharded_next(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+				   int64_t first_position, uint32_t lap, int max_ac_errors, void *cuda_stream,
+				   int64_t *n_prev);
+/* rank r's records of the latest scan: (*d_slots) + r * (*slot_stride), counts[r] of them (device memory
+ * owned by the library, valid until the next but one _end); counts holds `world` entries */
+int btbb_b200_find_ac_sharded_gather(btbb_b200_ctx *ctx, const btbb_b200_hit **d_slots, int64_t *slot_stride,
+				     int64_t *counts, int64_t *n_total);
+int btbb_b200_find_ac_sharded_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
+				  int64_t first_position, uint32_t lap, int max_ac_errors,
+				  btbb_b200_hit *d_all, int64_t max_all, int64_t *counts, int64_t *n_total, void *cuda_stream);
 
 /*
  * BR/EDR capture records (pcap, DLT 255) from batch results: the bytes btbb_pcap_create_file /

@@ -72,6 +72,8 @@ _PROTOS = {
     "btbb_b200_find_ac_dev_begin": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, _vp]),
     "btbb_b200_find_ac_dev_end": (_int, [_vp, C.POINTER(_i64)]),
     "btbb_b200_set_offset_bias": (_int, [_vp, _i64]),
+    "btbb_b200_set_profiling": (_int, [_vp, _int]),
+    "btbb_b200_last_scan_kernel_ms": (_int, [_vp, C.POINTER(C.c_float)]),
     "btbb_b200_find_ac_packed_dev": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64), _vp]),
     "btbb_b200_find_ac_enqueue": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, _vp, _vp]),
     "btbb_b200_find_ac_host": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64)]),
@@ -79,6 +81,15 @@ _PROTOS = {
     "btbb_b200_decode_host": (_int, [_vp, _vp, _i64, _vp, _i64, _int, _vp]),
     "btbb_b200_try_clocks_compact_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_decode_smallcall": (_int, [_vp, _int, _u32, C.c_uint8, _int, C.c_uint8, _int, _vp]),
+    "btbb_b200_shard_unique_id": (_int, [_vp]),
+    "btbb_b200_shard_init": (_int, [_vp, _vp, _int, _int, _i64, _int]),
+    "btbb_b200_shard_info": (_int, [_vp, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "btbb_b200_shard_destroy": (_int, [_vp]),
+    "btbb_b200_find_ac_sharded_begin": (_int, [_vp, _vp, _i64, _i64, _u32, _int, _vp]),
+    "btbb_b200_find_ac_sharded_end": (_int, [_vp, C.POINTER(_i64)]),
+    "btbb_b200_find_ac_sharded_next": (_int, [_vp, _vp, _i64, _i64, _u32, _int, _vp, C.POINTER(_i64)]),
+    "btbb_b200_find_ac_sharded_gather": (_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _vp, C.POINTER(_i64)]),
+    "btbb_b200_find_ac_sharded_dev": (_int, [_vp, _vp, _i64, _i64, _u32, _int, _vp, _i64, _vp, C.POINTER(_i64), _vp]),
     "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
@@ -227,6 +238,14 @@ class Context:
         check(rc, allow=(-4,))
         return n.value, rc
 
+    def set_profiling(self, on=True):
+        check(lib().btbb_b200_set_profiling(self.h, 1 if on else 0))
+
+    def last_scan_kernel_ms(self):
+        ms = C.c_float(0)
+        check(lib().btbb_b200_last_scan_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def set_offset_bias(self, bias):
         check(lib().btbb_b200_set_offset_bias(self.h, bias))
 
@@ -259,7 +278,7 @@ class Context:
 
     def decode_host(self, stream, pkts, mode=0):
         assert stream.dtype == np.uint8 and pkts.dtype == PKTIN_DTYPE
-        out = np.zeros(len(pkts) * (64 if mode == 1 else 1), dtype=DECODED_DTYPE)
+        out = np.zeros(len(pkts) * (64 if (mode & 0xff) == MODE_TRY_CLOCKS else 1), dtype=DECODED_DTYPE)
         check(lib().btbb_b200_decode_host(self.h, stream.ctypes.data, len(stream), pkts.ctypes.data, len(pkts),
                                           mode, out.ctypes.data))
         return out

@@ -69,6 +69,7 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	btbb_b200_shard_destroy(ctx);
 	bt_tables_free(ctx);
 	if (ctx->d_count) cudaFree(ctx->d_count);
 	if (ctx->d_tmp) cudaFree(ctx->d_tmp);
@@ -87,6 +88,7 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	for (int i = 0; i < 4; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
 	delete ctx->host_lock;
 	if (ctx->ev_reset) cudaEventDestroy(ctx->ev_reset);
+	for (int i = 0; i < 2; i++) if (ctx->prof_ev[i]) cudaEventDestroy(ctx->prof_ev[i]);
 	if (ctx->d_slab) cudaFree(ctx->d_slab);
 	if (ctx->d_slab_cnt) cudaFree(ctx->d_slab_cnt);
 	if (ctx->d_slab_base) cudaFree(ctx->d_slab_base);

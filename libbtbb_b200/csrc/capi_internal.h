@@ -33,6 +33,8 @@ struct bt_pending {
 	cudaStream_t st;
 };
 
+struct bt_shard;
+
 struct btbb_b200_ctx {
 	int device;
 	int table_k;                 /* tables hold every pattern of 1..table_k errors in bits 0..57 */
@@ -94,6 +96,9 @@ struct btbb_b200_ctx {
 	void *d_scratch[4];          /* grow-only device scratch of the host-buffer entry points */
 	size_t scratch_cap[4];
 	cudaEvent_t ev_reset;        /* host-buffer scan: the counter reset has been enqueued */
+	cudaEvent_t prof_ev[2];      /* btbb_b200_set_profiling: around the bulk scan kernel */
+	int prof_on, prof_valid;
+	bt_shard *shard;             /* multi-GPU state (sharded.cu), NULL until btbb_b200_shard_init */
 	std::mutex *host_lock;       /* serialises the host-buffer entry points, which share the scratch above */
 };
 

@@ -587,7 +587,9 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 			else if (inv) kern = inv2 ? vk::scan_known_v4<true, true, true, true> : vk::scan_known_v4<true, true, false, true>;
 			else kern = inv2 ? vk::scan_known_v4<false, true, true, true> : vk::scan_known_v4<false, true, false, true>;
 		}
+		if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[0], st);
 		kern<<<(unsigned)grid, vk::WARPS * 32, vk::SMEM_BYTES, st>>>(a);
+		if (ctx->prof_on) { cudaEventRecord(ctx->prof_ev[1], st); ctx->prof_valid = 1; }
 	} else if (use_v7) {
 		/* developer switch: v7 = multiply windows, v7f = funnel-shift windows; a trailing 'a'
 		 * selects layout<1> (table A by byte permute, 32 KiB map); s4 / s6 = inline slots */
@@ -637,7 +639,9 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 				cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
 			}
 		}
+		if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[0], st);
 		kern<<<(unsigned)grid, v7::WARPS * 32, smem, st>>>(a);
+		if (ctx->prof_on) { cudaEventRecord(ctx->prof_ev[1], st); ctx->prof_valid = 1; }
 		if (k45 && ctx->l2_persist_bytes) {
 			cudaStreamAttrValue av;
 			memset(&av, 0, sizeof(av));
@@ -1032,6 +1036,27 @@ extern "C" int btbb_b200_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
 {
 	if (!ctx || !n_hits) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_end: bad arguments");
 	return bt_find_ac_dev_end(ctx, n_hits);
+}
+
+/* measurement hook: CUDA events around the bulk scan kernel of every following scan, on its stream */
+extern "C" int btbb_b200_set_profiling(btbb_b200_ctx *ctx, int on)
+{
+	if (!ctx) return btbb_b200_set_error(BTBB_B200_EINVAL, "set_profiling: bad arguments");
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	if (on && !ctx->prof_ev[0]) {
+		BT_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[0]));
+		BT_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[1]));
+	}
+	ctx->prof_on = on != 0;
+	ctx->prof_valid = 0;
+	return BTBB_B200_OK;
+}
+
+extern "C" int btbb_b200_last_scan_kernel_ms(btbb_b200_ctx *ctx, float *ms)
+{
+	if (!ctx || !ms || !ctx->prof_valid) return btbb_b200_set_error(BTBB_B200_EINVAL, "last_scan_kernel_ms: no profiled scan");
+	BT_CUDA_TRY(cudaEventElapsedTime(ms, ctx->prof_ev[0], ctx->prof_ev[1]));
+	return BTBB_B200_OK;
 }
 
 extern "C" int btbb_b200_set_offset_bias(btbb_b200_ctx *ctx, int64_t bias)

@@ -151,3 +151,69 @@ class PeerGather:
         slots = self.buf[g]
         counts = slots.view(torch.int64)[:, 0, 0].tolist()
         return slots[:, 1:], counts
+
+
+class ShardedScan:
+    """The C ABI's multi-GPU scan (btbb_b200_shard_* / btbb_b200_find_ac_sharded_*, csrc/sharded.cu)
+    driven from a torch.distributed program: torch only carries the 128-byte NCCL unique id from
+    rank 0 to the others; the scan, the peer-memory exchange and the NCCL allgatherv form all live
+    in the library."""
+
+    def __init__(self, ctx, slot_records, group=None, nccl_only=False):
+        import ctypes as C
+        from . import binding as B
+        self.B, self.C, self.ctx = B, C, ctx
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.world = dist.get_world_size(self.group) if self.group is not None else 1
+        self.rank = dist.get_rank(self.group) if self.group is not None else 0
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            B.check(B.lib().btbb_b200_shard_unique_id(buf))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+            t = ident.to(dev)
+            dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0, group=self.group)
+            ident = t.cpu()
+        raw = (C.c_uint8 * 128)(*ident.tolist())
+        B.check(B.lib().btbb_b200_shard_init(ctx.h, raw, self.rank, self.world, int(slot_records), 1 if nccl_only else 0))
+        pm = C.c_int(0)
+        B.check(B.lib().btbb_b200_shard_info(ctx.h, None, None, C.byref(pm)))
+        self.peer_memory = bool(pm.value)
+        self.slot = int(slot_records)
+
+    def begin(self, d_ptr, search_length, first_position, lap=0xFFFFFFFF, k=2, stream=0):
+        self.B.check(self.B.lib().btbb_b200_find_ac_sharded_begin(self.ctx.h, d_ptr, search_length, first_position, lap, k, stream))
+
+    def end(self):
+        n = self.C.c_int64(0)
+        self.B.check(self.B.lib().btbb_b200_find_ac_sharded_end(self.ctx.h, self.C.byref(n)))
+        return n.value
+
+    def next(self, d_ptr, search_length, first_position, lap=0xFFFFFFFF, k=2, stream=0):
+        """end of the pending scan + begin of the next one; returns the finished scan's hit count"""
+        n = self.C.c_int64(0)
+        self.B.check(self.B.lib().btbb_b200_find_ac_sharded_next(self.ctx.h, d_ptr, search_length, first_position, lap, k, stream,
+                                                                 self.C.byref(n)))
+        return n.value
+
+    def gather(self):
+        """(device pointer of slot 0, slot stride in records, counts list, total)"""
+        C = self.C
+        slots, stride, total = C.c_void_p(0), C.c_int64(0), C.c_int64(0)
+        counts = (C.c_int64 * self.world)()
+        self.B.check(self.B.lib().btbb_b200_find_ac_sharded_gather(self.ctx.h, C.byref(slots), C.byref(stride), counts, C.byref(total)))
+        return slots.value, stride.value, list(counts), total.value
+
+    def scan_all(self, d_ptr, search_length, first_position, d_all_ptr, max_all, lap=0xFFFFFFFF, k=2, stream=0):
+        C = self.C
+        counts = (C.c_int64 * self.world)()
+        total = C.c_int64(0)
+        rc = self.B.lib().btbb_b200_find_ac_sharded_dev(self.ctx.h, d_ptr, search_length, first_position, lap, k, d_all_ptr, max_all,
+                                                       counts, C.byref(total), stream)
+        self.B.check(rc, allow=(-4,))
+        return list(counts), total.value, rc
+
+    def close(self):
+        self.B.check(self.B.lib().btbb_b200_shard_destroy(self.ctx.h))

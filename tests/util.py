@@ -26,7 +26,7 @@ _ref = None
 def oracle():
     global _oracle
     if _oracle is None:
-        src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "oracle.h")]
+        src = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "oracle.h", "synth_gen.c")]
         if not os.path.exists(ORACLE_SO) or any(os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in src):
             subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
         L = C.CDLL(ORACLE_SO)
@@ -52,6 +52,8 @@ def oracle():
         L.orc_hop_sequence.argtypes = [C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_uap_sieve.restype = None
         L.orc_uap_sieve.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_synth.restype = C.c_int
+        L.orc_synth.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _oracle = L
     return _oracle
 
