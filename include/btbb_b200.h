@@ -201,6 +201,17 @@ int btbb_b200_header_present_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, in
 				 const btbb_b200_pkt_in *d_pkts, int64_t n,
 				 uint8_t *d_present, void *cuda_stream);
 
+int btbb_b200_header_present_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
+				  const btbb_b200_pkt_in *pkts, int64_t n, uint8_t *present);
+
+/* Routing of the CLASSIC surface (include/btbb.h) only: btbb_find_ac calls that search at most
+ * find_ac_host_below positions (default 8192; -1 = never) and, unless packet_calls_on_gpu is set,
+ * the single-packet calls (btbb_decode_header / _payload, try_clock, crc_check, fhs / DM / ...,
+ * btbb_header_present) are answered by the host small-call path; everything else launches
+ * kernels.  The environment variable BTBB_B200_CLASSIC=gpu sets (-1, 1) at first use.  The batch
+ * entry points of this header are not affected: they always run on the GPU. */
+void btbb_b200_classic_config(int find_ac_host_below, int packet_calls_on_gpu);
+
 /*
  * UAP / CLK1-6 discovery from packet headers: btbb_uap_from_header (bluetooth_piconet.c:648-750)
  * as btbb_process_packet drives it in survey mode (:851-858), for many piconets at once

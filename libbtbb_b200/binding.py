@@ -91,6 +91,8 @@ _PROTOS = {
     "btbb_b200_find_ac_sharded_gather": (_int, [_vp, C.POINTER(_vp), C.POINTER(_i64), _vp, C.POINTER(_i64)]),
     "btbb_b200_find_ac_sharded_dev": (_int, [_vp, _vp, _i64, _i64, _u32, _int, _vp, _i64, _vp, C.POINTER(_i64), _vp]),
     "btbb_b200_header_present_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "btbb_b200_header_present_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "btbb_b200_classic_config": (None, [_int, _int]),
     "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_group_by_lap": (_i64, [_vp, _i64, _vp, _vp, _vp]),

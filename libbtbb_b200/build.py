@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libbtbb.so.1")
 STATIC = os.path.join(LIBDIR, "libbtbb.a")
-SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "decode_tables.cpp", "decode_host.cpp", "sieve.cu",
+SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "decode_tables.cpp", "decode_host.cpp", "find_ac_host.cpp", "sieve.cu",
            "hops.cu", "synth.cu", "compat.cu", "host_pack.cpp", "pcap_out.cpp", "sharded.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -78,6 +78,44 @@ def build(force=False, verbose=False, ptxas_verbose=False):
     return LIB
 
 
+FULL_LIB = os.path.join(LIBDIR, "full", "libbtbb.so.1")
+REF_UNITS = ["bluetooth_piconet.c", "bluetooth_le_packet.c", "companies.c", "pcap.c", "pcapng.c", "pcapng-bt.c"]
+
+
+def compose(reference_root="/root/reference", verbose=False):
+    """The COMPLETE libbtbb.so.1 surface (every symbol of upstream's btbb.h): this library's packet
+    layer plus upstream's own piconet / pcap / pcapng / LE translation units, compiled UNCHANGED
+    where they lie (lib/src/CMakeLists.txt:26-32 minus bluetooth_packet.c) and linked into
+    lib/full/libbtbb.so.1.  That is the file to hand to callers such as ubertooth-rx that also use
+    btbb_piconet_* / btbb_process_packet / btbb_pcap* / lell_* (INTEGRATION.md).  No reference source is copied
+    into this tree; without a checkout of upstream nothing is built and None is returned."""
+    src = os.path.join(reference_root, "lib", "src")
+    if not os.path.exists(os.path.join(src, "bluetooth_piconet.c")):
+        return None
+    build()
+    os.makedirs(os.path.dirname(FULL_LIB), exist_ok=True)
+    objs = []
+    for u in REF_UNITS:
+        o = os.path.join(OBJDIR, "upstream_" + u + ".o")
+        cmd = ["gcc", "-O2", "-fPIC", "-w", "-std=gnu90", "-I" + src, "-c", os.path.join(src, u), "-o", o]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+        objs.append(o)
+    ours = [os.path.join(OBJDIR, s + ".o") for s in _sources()]
+    cmd = [NVCC] + LDFLAGS + ours + objs + ["-o", FULL_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("linking lib/full/libbtbb.so.1 failed")
+    return FULL_LIB
+
+
 if __name__ == "__main__":
+    if "--compose-reference" in sys.argv:
+        i = sys.argv.index("--compose-reference")
+        root = sys.argv[i + 1] if i + 1 < len(sys.argv) and not sys.argv[i + 1].startswith("-") else "/root/reference"
+        print(compose(root, verbose="-v" in sys.argv))
+        sys.exit(0)
     build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_verbose="--ptxas-verbose" in sys.argv)
     print(LIB)

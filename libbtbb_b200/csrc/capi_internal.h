@@ -64,6 +64,7 @@ struct btbb_b200_ctx {
 	void *d_xp;                  /* ring of 16 x 128-byte exact-test parameter blocks (bulk kernel) */
 	unsigned xp_next;
 	bt_err_slot *d_err;          /* hash table, capacity 1 << err_log2 (NULL when table_k == 0) */
+	bt_err_slot *h_err;          /* host copy (small-call path of the classic btbb_find_ac) */
 	int err_log2;
 	long err_entries;
 	/* scratch owned by the context */
@@ -138,6 +139,13 @@ int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t s
 
 /* host_pack.cpp */
 extern "C" void bt_pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out);
+
+/* find_ac_host.cpp, decode_host.cpp: the small-call path of the classic single-packet surface */
+int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,
+		      int max_ac_errors, btbb_b200_hit *hit, int *found);
+int bt_decode_one_cpu(const char *symbols, int length, uint32_t clkn, uint8_t uap, int whitened, uint8_t type,
+		      int mode, btbb_b200_decoded *out);
+int bt_header_present_cpu(const char *symbols, int length);
 
 /* capi.cu */
 int bt_find_first_host(btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,

@@ -11,7 +11,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
+#include <shared_mutex>
 #include "../../include/btbb.h"
 #include "bt_math.h"
 #include "capi_internal.h"
@@ -47,8 +49,19 @@ struct btbb_packet {
 };
 static_assert(sizeof(btbb_packet) == 5952, "btbb_packet must keep the upstream layout");
 
-static std::mutex g_lock;
+/* ---- library state ----
+ * g_state guards the context pointer: every shim call holds it shared for its duration, btbb_init
+ * takes it exclusively when it has to (re)build the tables (the reference builds its syndrome map
+ * once, for the first non-zero k, :288-289).  GPU-path calls additionally serialise on g_gpu, because
+ * they share the context's device scratch.  The host small-call path is re-entrant, like the
+ * reference after btbb_init. */
+static std::shared_mutex g_state;
+static std::mutex g_gpu;
 static btbb_b200_ctx *g_ctx;
+/* routing of the classic calls (btbb_b200_classic_config): searches of at most this many positions
+ * and all single-packet calls are answered on the host (find_ac_host.cpp, decode_host.cpp) */
+static std::atomic<int> g_host_below{-2};      /* -2: not configured yet (read BTBB_B200_CLASSIC once) */
+static std::atomic<int> g_packet_gpu{0};
 
 static int env_device(void)
 {
@@ -56,22 +69,40 @@ static int env_device(void)
 	return e ? atoi(e) : 0;
 }
 
-/* The reference builds its syndrome map once, for the first non-zero k (:288-289). */
-static btbb_b200_ctx *get_ctx(int k_if_new)
+static void route_init(void)
 {
-	std::lock_guard<std::mutex> g(g_lock);
-	if (g_ctx && btbb_b200_table_errors(g_ctx) == 0 && k_if_new > 0) {
-		btbb_b200_destroy(g_ctx);
-		g_ctx = NULL;
+	if (g_host_below.load() != -2) return;
+	const char *e = getenv("BTBB_B200_CLASSIC");      /* "gpu": every classic call launches kernels */
+	if (e && !strcmp(e, "gpu")) { g_packet_gpu.store(1); g_host_below.store(-1); }
+	else g_host_below.store(8192);
+}
+
+/* caller holds g_state (shared); creates the context on first use */
+static btbb_b200_ctx *ctx_locked(std::shared_lock<std::shared_mutex> &lk, int k_if_new)
+{
+	if (g_ctx) return g_ctx;
+	lk.unlock();
+	{
+		std::unique_lock<std::shared_mutex> w(g_state);
+		if (!g_ctx && btbb_b200_create(env_device(), k_if_new, &g_ctx) != BTBB_B200_OK) {
+			fprintf(stderr, "libbtbb (B200): %s\n", btbb_b200_last_error());
+			g_ctx = NULL;
+		}
 	}
-	if (!g_ctx && btbb_b200_create(env_device(), k_if_new, &g_ctx) != BTBB_B200_OK) {
-		fprintf(stderr, "libbtbb (B200): %s\n", btbb_b200_last_error());
-		g_ctx = NULL;
-	}
+	lk.lock();
 	return g_ctx;
 }
 
 extern "C" {
+
+/* find_ac_host_below: btbb_find_ac calls searching at most this many positions run on the host
+ * (-1: never); packet_calls_on_gpu != 0: btbb_decode* / try_clock / crc_check / btbb_header_present
+ * launch kernels instead of taking the host small-call path */
+void btbb_b200_classic_config(int find_ac_host_below, int packet_calls_on_gpu)
+{
+	g_host_below.store(find_ac_host_below < -1 ? -1 : find_ac_host_below);
+	g_packet_gpu.store(packet_calls_on_gpu != 0);
+}
 
 int btbb_init(int max_ac_errors)
 {
@@ -79,7 +110,18 @@ int btbb_init(int max_ac_errors)
 		fprintf(stderr, "%s: max_ac_errors out of range\n", __FUNCTION__);
 		return -1;
 	}
-	return get_ctx(max_ac_errors) ? 0 : -2;
+	route_init();
+	std::unique_lock<std::shared_mutex> w(g_state);
+	if (g_ctx && btbb_b200_table_errors(g_ctx) == 0 && max_ac_errors > 0) {
+		std::lock_guard<std::mutex> g(g_gpu);
+		btbb_b200_destroy(g_ctx);
+		g_ctx = NULL;
+	}
+	if (!g_ctx && btbb_b200_create(env_device(), max_ac_errors, &g_ctx) != BTBB_B200_OK) {
+		fprintf(stderr, "libbtbb (B200): %s\n", btbb_b200_last_error());
+		g_ctx = NULL;
+	}
+	return g_ctx ? 0 : -2;
 }
 
 #ifndef BTBB_B200_RELEASE
@@ -154,11 +196,19 @@ uint64_t btbb_gen_syncword(const int LAP) { return bt_gen_syncword((uint32_t)LAP
 /* ---- access-code search ---- */
 static int find_first(char *stream, int search_length, uint32_t lap, int k, uint32_t *lap_out, uint8_t *ac_errors)
 {
-	btbb_b200_ctx *ctx = get_ctx(0);
+	route_init();
+	std::shared_lock<std::shared_mutex> lk(g_state);
+	btbb_b200_ctx *ctx = ctx_locked(lk, 0);
 	btbb_b200_hit h;
-	int found = 0;
+	int found = 0, rc;
 	if (!ctx) return -2;
-	if (bt_find_first_host(ctx, stream, search_length, lap, k, &h, &found) != BTBB_B200_OK) {
+	if (search_length <= g_host_below.load())
+		rc = bt_find_first_cpu(ctx, stream, search_length, lap, k, &h, &found);
+	else {
+		std::lock_guard<std::mutex> g(g_gpu);
+		rc = bt_find_first_host(ctx, stream, search_length, lap, k, &h, &found);
+	}
+	if (rc != BTBB_B200_OK) {
 		fprintf(stderr, "libbtbb (B200): %s\n", btbb_b200_last_error());
 		return -2;
 	}
@@ -196,22 +246,37 @@ int btbb_find_ac(char *stream, int search_length, uint32_t lap, int max_ac_error
 	return off;
 }
 
-/* ---- per-packet chain: one GPU launch per call ---- */
-static int run_chain(btbb_packet *p, int mode, int clock, btbb_b200_decoded *rec, int nrec)
+/* ---- per-packet chain: the host small-call path, or one GPU launch per call ---- */
+static int run_chain(btbb_packet *p, int mode, int clock, btbb_b200_decoded *rec)
 {
-	btbb_b200_ctx *ctx = get_ctx(0);
+	route_init();
+	const int whitened = btbb_packet_get_flag(p, BTBB_WHITENED);
+	if (!g_packet_gpu.load())
+		return bt_decode_one_cpu(p->symbols, p->length, (uint32_t)clock, p->UAP, whitened, p->packet_type, mode, rec) ? -1 : 0;
+	std::shared_lock<std::shared_mutex> lk(g_state);
+	btbb_b200_ctx *ctx = ctx_locked(lk, 0);
 	btbb_b200_pkt_in in;
 	if (!ctx) return -1;
 	memset(&in, 0, sizeof(in));
 	in.offset = 0; in.length = p->length; in.clkn = (uint32_t)clock;
-	in.uap = p->UAP; in.whitened = (uint8_t)btbb_packet_get_flag(p, BTBB_WHITENED);
+	in.uap = p->UAP; in.whitened = (uint8_t)whitened;
 	in.type = p->packet_type;
-	(void)nrec;
 	if (btbb_b200_decode_host(ctx, p->symbols, MAX_SYMBOLS, &in, 1, mode, rec) != BTBB_B200_OK) {
 		fprintf(stderr, "libbtbb (B200): %s\n", btbb_b200_last_error());
 		return -1;
 	}
 	return 0;
+}
+
+/* unfec13 of the 18 header triplets (:552-568): the header is "there" iff fewer than 18 / 4 disagree */
+static int header_fec_ok(const btbb_packet *p)
+{
+	int bad = 0;
+	for (int i = 0; i < 18; i++) {
+		const int t = (p->symbols[68 + 3 * i] & 1) + (p->symbols[69 + 3 * i] & 1) + (p->symbols[70 + 3 * i] & 1);
+		bad += (t == 1 || t == 2);
+	}
+	return bad < 18 / 4;
 }
 
 static void store_payload(btbb_packet *p, const btbb_b200_decoded *r)
@@ -221,7 +286,9 @@ static void store_payload(btbb_packet *p, const btbb_b200_decoded *r)
 	p->payload_llid = r->llid;
 	p->payload_flow = r->flow;
 	if (r->has_payload) btbb_packet_set_flag(p, BTBB_HAS_PAYLOAD, 1);
-	if (r->rv >= 2 && r->payload_length > 0 && r->payload_length <= 344)
+	/* the record was asked for with BTBB_B200_MODE_FLAG_RAW_PAYLOAD: it carries what the reference's
+	 * decoders leave in pkt->payload whatever rv says (bits they did not write read 0, as in a fresh packet) */
+	if (r->payload_length > 0 && r->payload_length <= 344)
 		for (int i = 0; i < r->payload_length * 8; i++)
 			p->payload[i] = (char)((r->payload[i >> 3] >> (i & 7)) & 1);
 }
@@ -229,7 +296,7 @@ static void store_payload(btbb_packet *p, const btbb_b200_decoded *r)
 uint8_t try_clock(int clock, btbb_packet *p)
 {
 	static thread_local btbb_b200_decoded rec[64];
-	if (run_chain(p, BTBB_B200_MODE_TRY_CLOCKS, 0, rec, 64)) return 0;
+	if (run_chain(p, BTBB_B200_MODE_TRY_CLOCKS, 0, rec)) return 0;
 	const btbb_b200_decoded *r = &rec[clock & 63];
 	if (!r->header_ok) return 0;          /* unfec13 failed: packet untouched (:1186-1187) */
 	p->UAP = r->uap;
@@ -240,7 +307,7 @@ uint8_t try_clock(int clock, btbb_packet *p)
 static int typed(int mode, int clock, btbb_packet *p)
 {
 	btbb_b200_decoded r;
-	if (run_chain(p, mode, clock, &r, 1)) return 0;
+	if (run_chain(p, mode | BTBB_B200_MODE_FLAG_RAW_PAYLOAD, clock, &r)) return 0;
 	store_payload(p, &r);
 	return r.rv;
 }
@@ -258,8 +325,8 @@ int btbb_decode_header(btbb_packet *p)
 {
 	btbb_b200_decoded r;
 	if (!btbb_packet_get_flag(p, BTBB_CLK6_VALID)) return 0;
-	if (run_chain(p, BTBB_B200_MODE_DECODE, (int)p->clkn, &r, 1)) return 0;
-	if (r.header_ok || r.header_packed)
+	if (run_chain(p, BTBB_B200_MODE_DECODE, (int)p->clkn, &r)) return 0;
+	if (header_fec_ok(p))      /* the reference writes packet_header once unfec13 has passed, whatever the HEC says (:1203-1209) */
 		for (int i = 0; i < 18; i++) p->packet_header[i] = (char)((r.header_packed >> i) & 1);
 	if (!r.header_ok) return 0;
 	p->packet_lt_addr = r.lt_addr; p->packet_type = r.type;
@@ -270,7 +337,7 @@ int btbb_decode_header(btbb_packet *p)
 int btbb_decode_payload(btbb_packet *p)
 {
 	btbb_b200_decoded r;
-	if (run_chain(p, BTBB_B200_MODE_PAYLOAD, (int)p->clkn, &r, 1)) return 0;
+	if (run_chain(p, BTBB_B200_MODE_PAYLOAD | BTBB_B200_MODE_FLAG_RAW_PAYLOAD, (int)p->clkn, &r)) return 0;
 	store_payload(p, &r);
 	btbb_packet_set_flag(p, BTBB_HAS_PAYLOAD, 1);
 	return r.rv;
@@ -313,24 +380,19 @@ int btbb_decode(btbb_packet *p)
 
 int btbb_header_present(const btbb_packet *p)
 {
-	btbb_b200_ctx *ctx = get_ctx(0);
+	route_init();
+	if (!g_packet_gpu.load())
+		return bt_header_present_cpu(p->symbols, p->length);
+	std::shared_lock<std::shared_mutex> lk(g_state);
+	btbb_b200_ctx *ctx = ctx_locked(lk, 0);
 	if (!ctx) return 0;
-	/* single packet: stage symbols, run the batch kernel on one record */
-	uint8_t *d_s = NULL, *d_r = NULL; btbb_b200_pkt_in *d_p = NULL;
+	std::lock_guard<std::mutex> g(g_gpu);
+	/* single packet through the batch kernel; the device scratch is the context's own */
 	btbb_b200_pkt_in in;
 	uint8_t res = 0;
 	memset(&in, 0, sizeof(in));
 	in.length = p->length;
-	if (cudaMalloc(&d_s, MAX_SYMBOLS) == cudaSuccess && cudaMalloc(&d_r, 1) == cudaSuccess &&
-	    cudaMalloc(&d_p, sizeof(in)) == cudaSuccess &&
-	    cudaMemcpy(d_s, p->symbols, MAX_SYMBOLS, cudaMemcpyHostToDevice) == cudaSuccess &&
-	    cudaMemcpy(d_p, &in, sizeof(in), cudaMemcpyHostToDevice) == cudaSuccess &&
-	    btbb_b200_header_present_dev(ctx, d_s, MAX_SYMBOLS, d_p, 1, d_r, NULL) == BTBB_B200_OK)
-		cudaMemcpy(&res, d_r, 1, cudaMemcpyDeviceToHost);
-	if (d_s) cudaFree(d_s);
-	if (d_r) cudaFree(d_r);
-	if (d_p) cudaFree(d_p);
-	return res;
+	return btbb_b200_header_present_host(ctx, p->symbols, MAX_SYMBOLS, &in, 1, &res) == BTBB_B200_OK ? res : 0;
 }
 
 char *tun_format(btbb_packet *p)

@@ -504,6 +504,28 @@ extern "C" int btbb_b200_decode_host(btbb_b200_ctx *ctx, const char *stream, int
 	return BTBB_B200_OK;
 }
 
+extern "C" int btbb_b200_header_present_host(btbb_b200_ctx *ctx, const char *stream, int64_t stream_length,
+					     const btbb_b200_pkt_in *pkts, int64_t n, uint8_t *present)
+{
+	if (!ctx || n < 0 || (n > 0 && (!stream || !pkts || !present)) || stream_length < 0)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "header_present_host: bad arguments");
+	if (n == 0) return BTBB_B200_OK;
+	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	std::lock_guard<std::mutex> guard(*ctx->host_lock);
+	void *d_s = NULL, *d_p = NULL, *d_o = NULL;
+	int rc = ensure_scratch(ctx, 0, (size_t)stream_length + 64, &d_s);
+	if (!rc) rc = ensure_scratch(ctx, 1, (size_t)n * sizeof(btbb_b200_pkt_in), &d_p);
+	if (!rc) rc = ensure_scratch(ctx, 2, (size_t)n, &d_o);
+	if (rc) return rc;
+	BT_CUDA_TRY(cudaMemcpy(d_s, stream, (size_t)stream_length, cudaMemcpyHostToDevice));
+	BT_CUDA_TRY(cudaMemcpy(d_p, pkts, (size_t)n * sizeof(btbb_b200_pkt_in), cudaMemcpyHostToDevice));
+	rc = btbb_b200_header_present_dev(ctx, static_cast<const uint8_t *>(d_s), stream_length, static_cast<const btbb_b200_pkt_in *>(d_p), n,
+					  static_cast<uint8_t *>(d_o), NULL);
+	if (rc) return rc;
+	BT_CUDA_TRY(cudaMemcpy(present, d_o, (size_t)n, cudaMemcpyDeviceToHost));
+	return BTBB_B200_OK;
+}
+
 extern "C" int btbb_b200_decode_smallcall(const char *symbols, int length, uint32_t clkn, uint8_t uap,
 					  int whitened, uint8_t type, int mode, btbb_b200_decoded *out)
 {

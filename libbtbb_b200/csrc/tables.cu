@@ -240,7 +240,7 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	}
 
 	/* --- open-addressing map --- */
-	ctx->d_err = NULL; ctx->err_log2 = 0;
+	ctx->d_err = NULL; ctx->h_err = NULL; ctx->err_log2 = 0;
 	if (!ents.empty()) {
 		int lg = 4;
 		while ((1UL << lg) < 2 * ents.size()) lg++;
@@ -254,6 +254,10 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_err, tab.size() * sizeof(bt_err_slot)));
 		BT_CUDA_TRY(cudaMemcpy(ctx->d_err, tab.data(), tab.size() * sizeof(bt_err_slot), cudaMemcpyHostToDevice));
 		ctx->err_log2 = lg;
+		/* host copy for the small-call path of the classic btbb_find_ac (find_ac_host.cpp) */
+		ctx->h_err = (bt_err_slot *)malloc(tab.size() * sizeof(bt_err_slot));
+		if (!ctx->h_err) return btbb_b200_set_error(BTBB_B200_ENOMEM, "tables: out of host memory");
+		memcpy(ctx->h_err, tab.data(), tab.size() * sizeof(bt_err_slot));
 	}
 	return BTBB_B200_OK;
 }
@@ -263,6 +267,7 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_tables) cudaFree(ctx->d_tables);
 	if (ctx->d_bloom) cudaFree(ctx->d_bloom);
 	if (ctx->d_err) cudaFree(ctx->d_err);
+	free(ctx->h_err); ctx->h_err = NULL;
 	if (ctx->d_lut2) cudaFree(ctx->d_lut2);
 	if (ctx->d_map2) cudaFree(ctx->d_map2);
 	if (ctx->d_lut4) cudaFree(ctx->d_lut4);

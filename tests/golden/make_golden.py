@@ -208,6 +208,28 @@ def gen_pcap():
     return out
 
 
+def gen_chain79():
+    """The whole chain of BASELINE configs[2] through the reference (oracle/_ref): access codes of a
+    79-channel capture, per hit btbb_decode with the true clock / UAP, the 64-clock try_clock + crc_check
+    sweep, and btbb_uap_from_header per piconet -> tests/golden/chain79.json."""
+    R = util.ref()
+    assert R.btbb_init(2) == 0
+    cfg, s, n = util.chain79_case()
+    hits = util.find_all(R, "ref", s, n, B.LAP_ANY, 2)
+    dec, sv, gs, laps = util.chain79_packets(cfg, hits)
+    recs = np.array([util.decode_one(R, "ref", s, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"])) for p in dec])
+    raw = np.array([util.decode_one_raw(R, "ref", s, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"])) for p in dec])
+    tc = np.array([util.try_clock_one(R, "ref", s, int(p["offset"]), int(p["length"]), c) for p in dec for c in range(64)])
+    st, rv = util.sieve_run(R, "ref", s, sv, gs)
+    out = {"blocks": 6, "symbols": n, "hits": len(hits), "hits_sha256": util.digest(hits), "decode_sha256": util.digest(recs),
+           "decode_raw_sha256": util.digest(raw), "try_clocks_sha256": util.digest(tc),
+           "rv_hist": {str(k): int(v) for k, v in zip(*np.unique(recs["rv"], return_counts=True))},
+           "piconets": len(gs) - 1, "piconets_resolved": int(((st["flags"] >> 2) & 1).sum()),
+           "sieve_sha256": [util.digest(st), util.digest(rv)]}
+    json.dump(out, open(os.path.join(HERE, "chain79.json"), "w"), indent=1)
+    return out
+
+
 def gen_hops():
     """Digests of windows of the reference's 2^27-entry hop table (gen_hop_pattern) for the addresses
     of tests/test_hops.py -> tests/golden/hops.json."""
@@ -230,6 +252,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hops":
         print(json.dumps(gen_hops()))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "chain79":
+        print(json.dumps(gen_chain79()))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "pcap":
         print(json.dumps(gen_pcap()))
         sys.exit(0)
@@ -248,6 +273,7 @@ if __name__ == "__main__":
     json.dump(gen_decode(), open(os.path.join(HERE, "decode.json"), "w"), indent=0)
     json.dump(gen_noise_types(), open(os.path.join(HERE, "noise_types.json"), "w"), indent=0)
     gen_sieve()
+    subprocess.run([sys.executable, __file__, "chain79"], check=True, capture_output=True)
     gen_pcap()
     gen_hops()
     print("golden fixtures written to", HERE)

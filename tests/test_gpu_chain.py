@@ -1,0 +1,82 @@
+"""BASELINE configs[2] end to end on the GPU, through the C ABI: access codes of a 79-channel
+interleaved capture ([block][79][4096], SURVEY.md 8d cfg 3) -> per hit btbb_decode_header +
+btbb_decode_payload with the true clock / UAP -> the 64-clock try_clock + crc_check sweep ->
+btbb_uap_from_header per piconet.  Every record is compared with the oracle, and the digests with
+the fixture the unmodified reference produced (tests/golden/chain79.json, make_golden.py)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import util
+from util import B
+
+pytestmark = pytest.mark.gpu
+
+
+def test_chain_on_79_channel_capture(gpu_ctx2, orc, product_lib):
+    import torch
+    g = json.load(open(os.path.join(util.GOLDEN, "chain79.json")))
+    cfg, s, n = util.chain79_case(g["blocks"])
+    assert n == g["symbols"]
+    lib, ctx = product_lib, gpu_ctx2
+    # the capture is generated on the device too, and everything below stays there
+    d = torch.empty(n + 63, dtype=torch.uint8, device="cuda")
+    B.check(lib.btbb_b200_synth_dev(C.byref(cfg), d.data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), s)
+    cap = 4096
+    d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    cnt, rc = ctx.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=B.LAP_ANY, k=2)
+    assert rc == 0 and cnt == g["hits"]
+    hits = d_hits[:cnt].cpu().numpy().reshape(-1).view(B.HIT_DTYPE)
+    assert orc.orc_init(2) == 0
+    assert hits.tobytes() == util.find_all(orc, "orc", s, n, B.LAP_ANY, 2).tobytes()
+    assert util.digest(hits) == g["hits_sha256"]
+
+    dec, sv, gs, laps = util.chain79_packets(cfg, hits)
+    d_pk = torch.from_numpy(dec.view(np.uint8)).cuda()
+    d_out = torch.zeros((cnt * 64, 372), dtype=torch.uint8, device="cuda")
+
+    def run(mode, count=cnt):
+        B.check(lib.btbb_b200_decode_dev(ctx.h, d.data_ptr(), n + 63, d_pk.data_ptr(), count, mode, d_out.data_ptr(), 0))
+        torch.cuda.synchronize()
+        return d_out[: count * (64 if (mode & 0xff) == 1 else 1)].cpu().numpy().reshape(-1).view(B.DECODED_DTYPE).copy()
+
+    # --- decode with the true clock / UAP ---
+    recs = run(B.MODE_DECODE)
+    for i, p in enumerate(dec):
+        want = util.decode_one(orc, "orc", s, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"]))
+        assert recs[i].tobytes() == want.tobytes(), (i, recs[i], want)
+    assert util.digest(recs) == g["decode_sha256"]
+    hist = {str(k): int(v) for k, v in zip(*np.unique(recs["rv"], return_counts=True))}
+    assert hist == g["rv_hist"] and hist.get("10", 0) > 150 and hist.get("1000", 0) > 50
+    raw = run(B.MODE_DECODE | B.MODE_FLAG_RAW_PAYLOAD)
+    assert util.digest(raw) == g["decode_raw_sha256"]
+    # --- 64-clock sweep ---
+    tc = run(B.MODE_TRY_CLOCKS)
+    for i in range(0, cnt, 7):
+        for c in range(64):
+            want = util.try_clock_one(orc, "orc", s, int(dec[i]["offset"]), int(dec[i]["length"]), c)
+            assert tc[i * 64 + c].tobytes() == want.tobytes(), (i, c)
+    assert util.digest(tc) == g["try_clocks_sha256"]
+    # --- UAP / CLK1-6 discovery per piconet ---
+    d_sv = torch.from_numpy(sv.view(np.uint8)).cuda()
+    d_gs = torch.from_numpy(gs).cuda()
+    d_st = torch.zeros((len(gs) - 1, 160), dtype=torch.uint8, device="cuda")
+    d_rv = torch.zeros(cnt, dtype=torch.int8, device="cuda")
+    B.check(lib.btbb_b200_uap_sieve_dev(ctx.h, d.data_ptr(), n + 63, d_sv.data_ptr(), cnt, d_gs.data_ptr(), len(gs) - 1,
+                                         d_st.data_ptr(), d_rv.data_ptr(), 0))
+    torch.cuda.synchronize()
+    st = d_st.cpu().numpy().reshape(-1).view(B.SIEVE_DTYPE)
+    rv = d_rv.cpu().numpy()
+    want_st, want_rv = util.sieve_run(orc, "orc", s, sv, gs)
+    assert st.tobytes() == want_st.tobytes() and rv.tobytes() == want_rv.tobytes()
+    assert [util.digest(st), util.digest(rv)] == g["sieve_sha256"]
+    assert int(((st["flags"] >> 2) & 1).sum()) == g["piconets_resolved"] == g["piconets"]
+    # the discovered UAP / clock are the planted ones
+    for gi, lap in enumerate(laps):
+        p = next(B.planted(cfg, int(q["offset"]) // util.CHAIN_BLK) for q in sv[gs[gi]:gs[gi + 1]])
+        assert st[gi]["uap"] == p.uap

@@ -11,8 +11,12 @@ from util import B
 pytestmark = pytest.mark.gpu
 
 
-def test_classic_find_ac_and_decode(product_lib, orc):
+@pytest.mark.parametrize("route", ["gpu", "host", "default"])
+def test_classic_find_ac_and_decode(product_lib, orc, route):
+    """route gpu: every classic call launches kernels; host: every call takes the host small-call path
+    (find_ac_host.cpp / decode_host.cpp); default: searches above 8192 positions on the GPU, the rest on the host."""
     L = product_lib
+    L.btbb_b200_classic_config(*{"gpu": (-1, 1), "host": (1 << 30, 0), "default": (8192, 0)}[route])
     L.btbb_packet_new.restype = C.c_void_p
     L.btbb_find_ac.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
     L.btbb_packet_set_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint8, C.c_uint32]
@@ -78,3 +82,4 @@ def test_classic_find_ac_and_decode(product_lib, orc):
     w = util.find_all(orc, "orc", s, 3000, 0x9E8B33, 0)
     assert off == (int(w[0]["offset"]) if len(w) else -1)
     L.btbb_packet_unref(pkt)
+    L.btbb_b200_classic_config(8192, 0)

@@ -225,3 +225,27 @@ def test_live_reference_decode_differential(orc):
         c = int(rng.integers(0, 64))
         assert util.try_clock_one(R, "ref", s, p.offset, L, c).tobytes() == \
             util.try_clock_one(orc, "orc", s, p.offset, L, c).tobytes()
+
+
+def test_chain79_fixture(orc):
+    """BASELINE configs[2] (79-channel capture): the oracle reproduces the reference's digests for the
+    whole chain -- hits, decode with the true clock, raw payload bytes, 64-clock sweep, UAP sieve."""
+    g = json.load(open(os.path.join(util.GOLDEN, "chain79.json")))
+    assert orc.orc_init(2) == 0
+    cfg, s, n = util.chain79_case(g["blocks"])
+    hits = util.find_all(orc, "orc", s, n, B.LAP_ANY, 2)
+    assert len(hits) == g["hits"] and util.digest(hits) == g["hits_sha256"]
+    dec, sv, gs, laps = util.chain79_packets(cfg, hits)
+    recs = np.array([util.decode_one(orc, "orc", s, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"])) for p in dec])
+    raw = np.array([util.decode_one_raw(orc, "orc", s, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"])) for p in dec])
+    tc = np.array([util.try_clock_one(orc, "orc", s, int(p["offset"]), int(p["length"]), c) for p in dec for c in range(64)])
+    assert util.digest(recs) == g["decode_sha256"] and util.digest(raw) == g["decode_raw_sha256"]
+    assert util.digest(tc) == g["try_clocks_sha256"]
+    st, rv = util.sieve_run(orc, "orc", s, sv, gs)
+    assert [util.digest(st), util.digest(rv)] == g["sieve_sha256"]
+    # the host small-call path (decode_core.h on the CPU) gives the same records
+    for i in range(0, len(dec), 5):
+        p = dec[i]
+        sym = np.ascontiguousarray(s[int(p["offset"]):int(p["offset"]) + int(p["length"])])
+        assert B.decode_smallcall(sym, len(sym), int(p["clkn"]), int(p["uap"]))[0].tobytes() == recs[i].tobytes()
+        assert B.decode_smallcall(sym, len(sym), mode=B.MODE_TRY_CLOCKS).tobytes() == tc[64 * i:64 * i + 64].tobytes()

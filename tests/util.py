@@ -274,3 +274,35 @@ def ev35_hunt(orc, rng, count):
     for i in range(count):
         clk, uap = int(rng.integers(0, 64)), int(rng.integers(0, 256))
         yield _craft(orc, rng, 13 if i % 4 else 7, clk, uap, rng.integers(0, 2, 3000, dtype=np.uint8)), clk, uap
+
+
+# ---- BASELINE configs[2]: the full chain on a 79-channel interleaved capture (SURVEY.md 8d cfg 3) ----
+CHAIN_BLK, CHAIN_CH = 4096, 79
+
+
+def chain79_case(blocks=6, ber=0.004, seed=B.DEFAULT_SEED):
+    """Capture laid out [block][79 channels][4096 symbols], every channel block carrying one planted
+    packet of a piconet-coherent capture (one UAP per LAP, CLK1-6 advancing with the slot)."""
+    n = blocks * CHAIN_CH * CHAIN_BLK
+    cfg = B.synth_cfg(n + 63, stride=CHAIN_BLK, n_laps=8, ber=ber, seed=seed, mix=("DM1", "DM3", "DH1", "FHS", "HV1"), piconets=True)
+    return cfg, B.synth_host(cfg), n
+
+
+def chain79_packets(cfg, hits):
+    """Per hit what the caller of the chain knows: the symbols left in the hit's channel block, the
+    slot as CLKN, slot % 79 as channel; for hits that are planted packets the true CLK1-6 / UAP
+    (else 0 / 0).  Returns (pkt_in for decode with the true clock, pkt_in for the sieve)."""
+    dec = np.zeros(len(hits), dtype=B.PKTIN_DTYPE)
+    for i, h in enumerate(hits):
+        off = int(h["offset"])
+        slot = off // CHAIN_BLK
+        p = B.planted(cfg, slot)
+        dec[i]["offset"], dec[i]["length"], dec[i]["whitened"] = off, min(3125, (slot + 1) * CHAIN_BLK - off), 1
+        if p.offset == off:
+            dec[i]["clkn"], dec[i]["uap"] = p.clk6, p.uap
+        dec[i]["reserved"] = slot % CHAIN_CH
+    order, gs, laps = B.group_by_lap(hits)
+    sv = dec[order].copy()
+    sv["clkn"] = sv["offset"] // CHAIN_BLK
+    sv["uap"] = 0
+    return dec, sv, gs, laps
