@@ -66,19 +66,29 @@ __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 	return v;
 }
 
-/* raw words [w_begin, w_end) (multiples of 16) from 16-symbol chunks of the aligned base */
+/* raw words [w_begin, w_end) (multiples of 16) from 16-symbol chunks of the aligned base; the loads of
+ * up to NB iterations are issued back to back before the first one is used */
+template <int NB>
 __device__ __forceinline__ void ingest(btd_pkt &P, const uint4 *base, int sh, int length, int w_begin, int w_end, int lane)
 {
-	for (int w0 = w_begin; w0 < w_end; w0 += 16) {
-		const int c = 2 * w0 + lane;
-		const uint32_t m = btd_chunk_mask(c, sh, length);
-		uint32_t h = 0;
-		if (m) {
-			const uint4 v = ld_stream(base + c);
-			h = btd_pack16(v.x, v.y, v.z, v.w) & m;
+	for (int w0 = w_begin; w0 < w_end; w0 += 16 * NB) {
+		uint4 v[NB];
+		uint32_t m[NB];
+		#pragma unroll
+		for (int i = 0; i < NB; i++) {
+			const int c = 2 * (w0 + 16 * i) + lane;
+			m[i] = w0 + 16 * i < w_end ? btd_chunk_mask(c, sh, length) : 0u;
+			v[i] = make_uint4(0, 0, 0, 0);
+			if (m[i]) v[i] = ld_stream(base + c);
 		}
-		const uint32_t hi = __shfl_down_sync(FULL, h, 1);
-		if (!(lane & 1)) P.raw[w0 + (lane >> 1)] = h | (hi << 16);
+		#pragma unroll
+		for (int i = 0; i < NB; i++) {
+			if (w0 + 16 * i < w_end) {
+				const uint32_t h = btd_pack16(v[i].x, v[i].y, v[i].z, v[i].w) & m[i];
+				const uint32_t hi = __shfl_down_sync(FULL, h, 1);
+				if (!(lane & 1)) P.raw[w0 + 16 * i + (lane >> 1)] = h | (hi << 16);
+			}
+		}
 	}
 }
 
@@ -129,17 +139,38 @@ __device__ __forceinline__ void build_dp(const btd_pkt &P, const uint16_t *nib, 
 	if (lane == 0) dp[0] = 0;
 }
 
-/* first candidate in [lo, hi) that passes, all lanes working on the same search */
-__device__ __forceinline__ int coop_search(const btd_ctx &c, const btd_pkt &P, int pend, int clock, uint32_t uap,
+/* first candidate in [lo, hi) that passes, all lanes working on the same search.  The fhs search is one
+ * candidate clock per lane.  The length searches (EV3 / EV5: lengths 3..181, EV4: 2..121) take eight
+ * consecutive lengths per lane: one 128-bit load of the packet's prefix table, one of the whitening
+ * table's row, eight 16-bit compares, one ballot. */
+__device__ __forceinline__ int coop_search(const btd_ctx &c, const btd_pkt &P, int pend, int q18, uint32_t uap,
 					   int lo, int hi, int lane)
 {
-	for (int b = lo; b < hi; b += 32) {
-		const int cand = b + lane;
-		const bool ok = cand < hi && btd_cand_ok(c, P, pend, clock, uap, cand);
-		const uint32_t m = __ballot_sync(FULL, ok);
-		if (m) return b + __ffs(m) - 1;
+	if (pend == BTD_PEND_FHS) {
+		const int cand = lo + lane;
+		const uint32_t m = __ballot_sync(FULL, cand < hi && btd_cand_ok(c, P, pend, q18, uap, cand));
+		return m ? lo + __ffs(m) - 1 : -1;
 	}
-	return -1;
+	const uint16_t *dp = pend == BTD_PEND_EV35 ? P.dp_first8 : P.dp_fec0;
+	uint4 d = *reinterpret_cast<const uint4 *>(dp + 8 * lane);
+	if (c.whitened) {
+		const uint4 w = __ldg(reinterpret_cast<const uint4 *>(c.wp + q18 * BTD_LMAX + 8 * lane));
+		d.x ^= w.x; d.y ^= w.y; d.z ^= w.z; d.w ^= w.w;
+	}
+	const uint32_t want = bt_crc16_init(uap);
+	const uint32_t v[4] = {d.x, d.y, d.z, d.w};
+	uint32_t mine = 0;
+	#pragma unroll
+	for (int t = 0; t < 8; t++) {
+		const uint32_t x = (t & 1) ? v[t >> 1] >> 16 : v[t >> 1] & 0xffffu;
+		const int L = 8 * lane + t;
+		if (x == want && L >= lo && L < hi) mine |= 1u << t;
+	}
+	const uint32_t m = __ballot_sync(FULL, mine != 0);
+	if (!m) return -1;
+	const int src = __ffs(m) - 1;
+	const uint32_t bits = __shfl_sync(FULL, mine, src);
+	return 8 * src + __ffs(bits) - 1;
 }
 
 /* crc_check / decode_payload / one decoder for this lane's (clock, UAP, type); searches are shared */
@@ -149,16 +180,16 @@ __device__ __forceinline__ void evaluate(const btd_ctx &c, const btd_pkt &P, btd
 	btd_eval_begin(c, P, s, kind);
 	int found = -1;
 	if (UNIFORM) {
-		if (s.pend) found = coop_search(c, P, s.pend, s.clock, s.uap, s.s_lo, s.s_hi, lane);
+		if (s.pend) found = coop_search(c, P, s.pend, btd_q18(c, s.clock), s.uap, s.s_lo, s.s_hi, lane);
 	} else {
 		uint32_t pm = __ballot_sync(FULL, s.pend != BTD_PEND_NONE);
 		while (pm) {
 			const int o = __ffs(pm) - 1;
 			pm &= pm - 1;
-			const int pend = __shfl_sync(FULL, s.pend, o), clock = __shfl_sync(FULL, s.clock, o);
+			const int pend = __shfl_sync(FULL, s.pend, o), q18 = btd_q18(c, __shfl_sync(FULL, s.clock, o));
 			const uint32_t uap = __shfl_sync(FULL, s.uap, o);
 			const int lo = __shfl_sync(FULL, s.s_lo, o), hi = __shfl_sync(FULL, s.s_hi, o);
-			const int f = coop_search(c, P, pend, clock, uap, lo, hi, lane);
+			const int f = coop_search(c, P, pend, q18, uap, lo, hi, lane);
 			if (lane == o) found = f;
 		}
 	}
@@ -166,7 +197,7 @@ __device__ __forceinline__ void evaluate(const btd_ctx &c, const btd_pkt &P, btd
 }
 
 template <int OUT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
+__global__ void __launch_bounds__(WARPS * 32, OUT == OUT_FULL64 ? 1 : 3) decode_kernel(const dec_args a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	btd_small_tables *s_small = reinterpret_cast<btd_small_tables *>(smem);
@@ -206,7 +237,7 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
 		__syncwarp();
 		if (lane == 0) { P.sh = sh; P.length = length; }
 		/* ---- header part: 512 symbols from the aligned base ---- */
-		ingest(P, base, sh, length, 0, 16, lane);
+		ingest<1>(P, base, sh, length, 0, 16, lane);
 		__syncwarp();
 		uint32_t hdr, hdr_ok;
 		{
@@ -214,7 +245,10 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
 			if (lane < 18) btd_vote3(P, 68, lane, &bit, &bad);
 			hdr = __ballot_sync(FULL, bit) & 0x3ffffu;
 			hdr_ok = __popc(__ballot_sync(FULL, bad)) < 18 / 4;      /* unfec13: be < length / 4 (:563-567) */
-			if (lane == 0) { P.hdr = hdr; P.hdr_ok = (int)hdr_ok; }
+			if (lane == 0) {
+				P.hdr = hdr; P.hdr_ok = (int)hdr_ok;
+				P.f8[0] = P.f8[1] = btd_bits(P.raw, sh + 122, 8) * 0x01010101u;
+			}
 		}
 		__syncwarp();
 		/* ---- which packet types are in play ---- */
@@ -243,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
 			int w_end = (sh + nd.symbols + 31) / 32 + 1;
 			w_end = (w_end + 15) & ~15;
 			if (w_end > BTD_RAW_WORDS - 1) w_end = BTD_RAW_WORDS - 1;
-			ingest(P, base, sh, length, 16, w_end, lane);
+			ingest<6>(P, base, sh, length, 16, w_end, lane);
 		}
 		__syncwarp();
 		/* ---- clock-independent work ---- */
@@ -282,7 +316,10 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
 				evaluate<true>(c, P, s, kind, lane);
 			}
 			const int nbits = btd_emit_bits(s, a.raw_payload);
-			const int q18 = btd_q(c, s.pay_clk, 18);
+			const int q18 = btd_q18(c, s.pay_clk);
+			const uint32_t *sb;
+			int pos0, step;
+			btd_src_desc(P, s.src, &sb, &pos0, &step);
 			uint32_t *o = reinterpret_cast<uint32_t *>(&a.out[p]);
 			#pragma unroll
 			for (int i = 0; i < 3; i++) {
@@ -290,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
 				if (w < REC_WORDS) {
 					uint32_t v;
 					if (w < 7) v = btd_record_word(s, header_ok, hp, w);
-					else v = btd_pay_word(c, P, s.src, (q18 + 32 * (w - 7)) % 127, w - 7, nbits);
+					else v = btd_pay_word(c, sb, pos0 + step * (w - 7), (q18 + 32 * (w - 7)) % 127, nbits - 32 * (w - 7));
 					o[w] = v;
 				}
 			}
@@ -306,14 +343,36 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const dec_args a)
 					/* the previous bulk store has to be done reading the staging buffer */
 					if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 					__syncwarp();
+					{
+						uint4 *z = reinterpret_cast<uint4 *>(stage);
+						for (int i = lane; i < STAGE_BYTES / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+					}
+					__syncwarp();
 					uint32_t *rec = stage + lane * REC_WORDS;      /* 93 words apart: conflict-free */
 					#pragma unroll
 					for (int w = 0; w < 7; w++) rec[w] = btd_record_word(s, (int)hdr_ok, 0, w);
+					/* payload: only the words that carry bits; the bit source is a pointer, a start bit and a
+					 * stride, so every lane runs the same instructions whatever its packet type is */
 					const int nbits = btd_emit_bits(s, a.raw_payload);
-					int q = btd_q(c, s.pay_clk, 18);
-					for (int j = 0; j < REC_WORDS - 7; j++) {
-						rec[7 + j] = btd_pay_word(c, P, s.src, q, j, nbits);
-						q += 32; if (q >= 127) q -= 127;
+					if (nbits > 0) {
+						const int nw = (nbits + 31) >> 5;
+						int q = btd_q18(c, s.pay_clk);
+						const uint32_t *sb;
+						int pos, step;
+						btd_src_desc(P, s.src, &sb, &pos, &step);
+						const uint32_t sh32 = (uint32_t)pos & 31u, adv = (uint32_t)step >> 5;
+						const uint32_t *wp = sb + (pos >> 5);
+						uint32_t lo_w = wp[0];
+						for (int j = 0; j < nw; j++) {
+							const uint32_t hi_w = wp[1];
+							uint32_t d = __funnelshift_r(lo_w, hi_w, sh32);
+							if (c.whitened) d ^= s_small->wrot[q];
+							if (j == nw - 1 && (nbits & 31)) d &= (1u << (nbits & 31)) - 1u;
+							rec[7 + j] = d;
+							if (adv) lo_w = hi_w;
+							wp += adv;
+							q += 32; if (q >= 127) q -= 127;
+						}
 					}
 					unsigned char *dst = reinterpret_cast<unsigned char *>(&a.out[p * 64 + 32 * round]);
 					if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {

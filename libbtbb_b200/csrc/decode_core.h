@@ -44,6 +44,7 @@ struct btd_small_tables {
 	uint32_t wrot[128];       /* wrot[p]: 32 whitening bits starting at sequence position p < 127 */
 	uint16_t wp20[64];        /* wp[(phase[c] + 18) % 127][20]: the fhs clock search */
 	uint8_t phase[64];        /* sequence position where the LFSR state is 0x40 | clk */
+	uint8_t q18[64];          /* (phase[clk] + 18) % 127: where the payload's whitening starts */
 	uint8_t fec_col[16];      /* parity column of each FEC 2/3 data bit */
 };
 struct btd_tables {
@@ -62,14 +63,17 @@ struct btd_ctx {
 
 /* clock-independent state of one packet */
 struct btd_pkt {
+	/* CRC prefix tables first: 16-byte aligned, the two that length searches walk padded to 256 entries
+	 * so that a warp can fetch eight consecutive entries per lane */
+	uint16_t dp_first8[256], dp_fec0[256], dp_raw[BTD_LMAX], dp_fec80[16];
 	uint32_t raw[BTD_RAW_WORDS];       /* bit (sh + i) = symbol i, 0 past `length` */
 	uint32_t fec0[BTD_FEC_WORDS];      /* corrected data bits of the FEC 2/3 blocks from symbol 122 */
 	uint32_t fec80[5];                 /* ... from symbol 202 (DV, :914) */
 	uint32_t hv1[4];                   /* FEC 1/3 vote of the 240 symbols at 122 */
+	uint32_t f8[2];                    /* the first eight payload symbols, replicated (EV3 / EV5 quirk) */
 	uint32_t hdr;                      /* 18 voted header bits */
 	int sh, length, hdr_ok, hv1_ok;
 	int fail0, fail80;                 /* index of the first uncorrectable block (or a large value) */
-	uint16_t dp_raw[BTD_LMAX], dp_fec0[232], dp_first8[184], dp_fec80[16];
 };
 
 /* per (packet, clock) result */
@@ -173,6 +177,7 @@ BT_HD int btd_q(const btd_ctx &c, int clock, int pos)
 {
 	return ((int)c.s->phase[clock & 63] + pos) % 127;
 }
+BT_HD int btd_q18(const btd_ctx &c, int clock) { return (int)c.s->q18[clock & 63]; }
 
 /* dewhitening bits for payload / header position pos .. pos + n (n <= 32) */
 BT_HD uint32_t btd_white(const btd_ctx &c, int clock, int pos, int n)
@@ -246,7 +251,7 @@ BT_HD void btd_fhs_begin(const btd_ctx &c, const btd_pkt &p, btd_lane &s)
 	if (size < 240) { s.rv = 1; return; }
 	if (p.fail0 < 16) { s.rv = 0; return; }
 	s.src = BTD_SRC_FEC0; s.wbits = 160; s.pay_clk = s.clock;
-	if (btd_check(c, p.dp_fec0, btd_q(c, s.clock, 18), 20, s.uap)) { s.rv = 1000; return; }
+	if (btd_check(c, p.dp_fec0, btd_q18(c, s.clock), 20, s.uap)) { s.rv = 1000; return; }
 	s.pend = BTD_PEND_FHS; s.s_lo = 32; s.s_hi = 64;
 }
 
@@ -300,7 +305,7 @@ BT_HD void btd_dm(const btd_ctx &c, const btd_pkt &p, btd_lane &s)
 	if (nbits > size) { s.rv = 1; return; }      /* bits against symbols, as the reference (:944) */
 	if ((dv ? p.fail80 : p.fail0) < (nbits + 9) / 10) { s.rv = 0; return; }
 	s.src = dv ? BTD_SRC_FEC80 : BTD_SRC_FEC0; s.pay_clk = s.clock; s.wbits = nbits;
-	s.rv = btd_check(c, dv ? p.dp_fec80 : p.dp_fec0, btd_q(c, s.clock, 18), s.plen, s.uap) ? 10 : 2;
+	s.rv = btd_check(c, dv ? p.dp_fec80 : p.dp_fec0, btd_q18(c, s.clock), s.plen, s.uap) ? 10 : 2;
 }
 
 /* DH (:962-1011) */
@@ -319,7 +324,7 @@ BT_HD void btd_dh(const btd_ctx &c, const btd_pkt &p, btd_lane &s)
 	if (nbits > size) { s.rv = 1; return; }
 	s.src = BTD_SRC_RAW; s.pay_clk = s.clock; s.wbits = nbits;
 	if (s.type == 9) { s.rv = 2; return; }
-	s.rv = btd_check(c, p.dp_raw, btd_q(c, s.clock, 18), s.plen, s.uap) ? 10 : 2;
+	s.rv = btd_check(c, p.dp_raw, btd_q18(c, s.clock), s.plen, s.uap) ? 10 : 2;
 }
 
 /* EV3 (:1013-1042) / EV5 (:1099-1128): every candidate length L in [3, min(maxlength, Lstop)) is one
@@ -383,19 +388,15 @@ BT_HD void btd_hv(const btd_pkt &p, btd_lane &s)
 	s.rv = 2;
 }
 
-/* one candidate of a pending search */
-BT_HD bool btd_cand_ok(const btd_ctx &c, const btd_pkt &p, int pend, int clock, uint32_t uap, int cand)
+/* one candidate of a pending search; q18 = btd_q18 of the clock the search belongs to */
+BT_HD bool btd_cand_ok(const btd_ctx &c, const btd_pkt &p, int pend, int q18, uint32_t uap, int cand)
 {
-	switch (pend) {
-	case BTD_PEND_FHS: {
+	if (pend == BTD_PEND_FHS) {
 		uint32_t v = p.dp_fec0[20];
 		if (c.whitened) v ^= c.s->wp20[cand & 63];
 		return v == bt_crc16_init(uap);
 	}
-	case BTD_PEND_EV35: return btd_check(c, p.dp_first8, btd_q(c, clock, 18), cand, uap);
-	case BTD_PEND_EV4:  return btd_check(c, p.dp_fec0, btd_q(c, clock, 18), cand, uap);
-	default: return false;
-	}
+	return btd_check(c, pend == BTD_PEND_EV35 ? p.dp_first8 : p.dp_fec0, q18, cand, uap);
 }
 
 /* begin: everything up to a pending search (s.pend != 0) or a final s.rv */
@@ -466,7 +467,7 @@ BT_HD void btd_eval_end(const btd_pkt &p, btd_lane &s, int kind, int found)
 BT_HD void btd_try_clock(const btd_ctx &c, const btd_pkt &p, btd_lane &s)
 {
 	if (!p.hdr_ok) return;      /* unfec13 failed: UAP / type stay as they were (0 in a fresh packet) */
-	const uint32_t hp = p.hdr ^ btd_white(c, s.clock, 0, 18);
+	const uint32_t hp = p.hdr ^ (c.whitened ? c.s->wrot[c.s->phase[s.clock & 63]] & 0x3ffffu : 0u);
 	s.uap = bt_uap_from_hec(hp & 0x3ffu, hp >> 10);
 	s.type = (hp >> 3) & 15u;
 }
@@ -495,20 +496,27 @@ BT_HD int btd_emit_bits(const btd_lane &s, int raw_payload)
 	return s.wbits < nb ? s.wbits : nb;
 }
 
-/* payload word j (bytes 4j .. 4j + 3 of the record's payload[]); q = (phase[pay_clk] + 18 + 32 j) % 127 */
-BT_HD uint32_t btd_pay_word(const btd_ctx &c, const btd_pkt &p, int src, int q, int j, int nbits)
+/* where a record's payload bits come from: word array, first bit, bits to advance per 32-bit word
+ * (0 for the EV3 / EV5 quirk, where every byte is dewhitened from the same eight symbols) */
+BT_HD void btd_src_desc(const btd_pkt &p, int src, const uint32_t **base, int *pos0, int *step)
 {
-	const int left = nbits - 32 * j;
-	if (left <= 0) return 0;
-	uint32_t d;
+	*step = 32; *pos0 = 0;
 	switch (src) {
-	case BTD_SRC_FEC0:   d = btd_bits(p.fec0, 32 * j, 32); break;
-	case BTD_SRC_FEC80:  d = btd_bits(p.fec80, 32 * j, 32); break;
-	case BTD_SRC_RAW:    d = btd_bits(p.raw, p.sh + 122 + 32 * j, 32); break;
-	case BTD_SRC_HV1:    d = p.hv1[j & 3]; break;
-	case BTD_SRC_FIRST8: d = btd_bits(p.raw, p.sh + 122, 8) * 0x01010101u; break;
-	default: d = 0;
+	case BTD_SRC_FEC0:   *base = p.fec0; break;
+	case BTD_SRC_FEC80:  *base = p.fec80; break;
+	case BTD_SRC_RAW:    *base = p.raw; *pos0 = p.sh + 122; break;
+	case BTD_SRC_HV1:    *base = p.hv1; break;
+	case BTD_SRC_FIRST8: *base = p.f8; *step = 0; break;
+	default:             *base = p.f8; *step = 0; break;      /* nothing to emit: the caller's bit count is 0 */
 	}
+}
+
+/* payload word j (bytes 4j .. 4j + 3 of the record's payload[]): pos = pos0 + step * j,
+ * q = (q18 of pay_clk + 32 j) % 127, left = payload bits not yet emitted */
+BT_HD uint32_t btd_pay_word(const btd_ctx &c, const uint32_t *base, int pos, int q, int left)
+{
+	if (left <= 0) return 0;      /* (also keeps the read inside the source array) */
+	uint32_t d = btd_bits(base, pos, 32);
 	if (c.whitened) d ^= c.s->wrot[q];
 	return left >= 32 ? d : d & ((1u << left) - 1u);
 }

@@ -34,6 +34,7 @@ void host_load(btd_pkt &p, const btd_tables *T, const char *symbols, int length,
 		hdr |= b << i; bad += (int)d;
 	}
 	p.hdr = hdr; p.hdr_ok = bad < 18 / 4;
+	p.f8[0] = p.f8[1] = btd_bits(p.raw, 122, 8) * 0x01010101u;
 	p.hv1_ok = 0;
 	if (n.hv1) {
 		bad = 0;
@@ -76,8 +77,9 @@ void host_load(btd_pkt &p, const btd_tables *T, const char *symbols, int length,
 
 int run_search(const btd_ctx &c, const btd_pkt &p, const btd_lane &s)
 {
+	const int q18 = btd_q18(c, s.clock);
 	for (int cand = s.s_lo; cand < s.s_hi; cand++)
-		if (btd_cand_ok(c, p, s.pend, s.clock, s.uap, cand)) return cand;
+		if (btd_cand_ok(c, p, s.pend, q18, s.uap, cand)) return cand;
 	return -1;
 }
 
@@ -87,10 +89,12 @@ void emit(const btd_ctx &c, const btd_pkt &p, const btd_lane &s, int header_ok, 
 	uint32_t *w = reinterpret_cast<uint32_t *>(o);
 	for (int i = 0; i < 7; i++) w[i] = btd_record_word(s, header_ok, hp, i);
 	const int nbits = btd_emit_bits(s, raw_payload);
-	int q = btd_q(c, s.pay_clk, 18);
+	const uint32_t *base;
+	int pos, step, q = btd_q18(c, s.pay_clk);
+	btd_src_desc(p, s.src, &base, &pos, &step);
 	for (int j = 0; j < 86; j++) {
-		w[7 + j] = btd_pay_word(c, p, s.src, q, j, nbits);
-		q += 32; if (q >= 127) q -= 127;
+		w[7 + j] = btd_pay_word(c, base, pos, q, nbits - 32 * j);
+		pos += step; q += 32; if (q >= 127) q -= 127;
 	}
 }
 

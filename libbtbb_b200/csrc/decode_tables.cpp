@@ -58,6 +58,7 @@ void build()
 			t.wp[q * BTD_LMAX + L] = x;
 		}
 	}
+	for (int c = 0; c < 64; c++) t.s.q18[c] = (uint8_t)((t.s.phase[c] + 18) % 127);
 	for (int c = 0; c < 64; c++)
 		t.s.wp20[c] = t.wp[((t.s.phase[c] + 18) % 127) * BTD_LMAX + 20];
 }
