@@ -307,12 +307,44 @@ int btbb_b200_find_ac_sharded_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, i
 				  btbb_b200_hit *d_all, int64_t max_all, int64_t *counts, int64_t *n_total, void *cuda_stream);
 
 /*
+ * ---- hop sequence and CLK1-27 discovery (bluetooth_piconet.c:311-362, :455-499, :575-645) ----
+ */
+typedef struct btbb_b200_hop_cfg {
+	uint32_t address;       /* (UAP << 24 | LAP) & 0xfffffff, as gen_hop_pattern passes it (:371-372) */
+	uint8_t  afh;           /* BTBB_IS_AFH: only the channels of afh_map are in the register bank (precalc :171-193) */
+	uint8_t  aliased;       /* winnow only: observed channels are aliased into 26..50 (aliased_channel :449-452) */
+	uint8_t  pad[2];
+	uint8_t  afh_map[10];   /* bit c % 8 of byte c / 8 = channel c in use (btbb_piconet_set_afh_map) */
+	uint8_t  pad2[2];
+} btbb_b200_hop_cfg;
+
+/* gen_hops (:311-362): entries [first, first + n) of the 2^27-entry channel sequence (index = CLK1-27),
+ * written to device memory.  Any range on its own; 2^27 entries are the reference's whole table. */
+int btbb_b200_hop_sequence_dev(btbb_b200_ctx *ctx, const btbb_b200_hop_cfg *cfg, int64_t first, int64_t n,
+			       uint8_t *d_out, void *cuda_stream);
+/*
+ * Hop reversal: btbb_init_hop_reversal's candidate list (init_candidates :455-472: every CLK1-27 value
+ * whose low six bits are known_clk6) filtered by n_obs observed hops as channel_winnow does
+ * (:575-611): candidate c survives observation j iff sequence[(c + indices[j]) mod 2^27] (aliased if
+ * cfg->aliased) == channels[j].  No 128 MiB table is built; the hop selection is evaluated per
+ * candidate.  candidates[] receives the survivors of ALL observations in ascending order (the order of
+ * the reference's list), *n_candidates their number (BTBB_B200_EOVERFLOW if more than
+ * max_candidates); survivors_after[j] (n_obs entries, may be NULL) = candidates left after
+ * observations 0..j -- pn->num_candidates after the reference's j-th channel_winnow call, which lets
+ * a caller reproduce btbb_winnow's stop at <= 1 (:622-623).  Host arrays in, host arrays out.
+ */
+int btbb_b200_hop_winnow(btbb_b200_ctx *ctx, const btbb_b200_hop_cfg *cfg, uint32_t known_clk6, int n_obs,
+			 const int32_t *indices, const uint8_t *channels, uint32_t *candidates, int64_t max_candidates,
+			 int64_t *n_candidates, int32_t *survivors_after);
+
+/*
  * BR/EDR capture records (pcap, DLT 255) from batch results: the bytes btbb_pcap_create_file /
  * btbb_pcap_append_packet (pcap.c:74-100, 176-209; record layout pcap-common.h:84-97) write,
  * serialised from btbb_b200_hit + btbb_b200_decoded instead of from a btbb_packet.  meta carries
  * what the reference takes from its arguments and from btbb_packet_set_data / _set_transport /
- * _set_modulation.  Host formatting only.  A packet whose payload decode failed (rv < 2) gets
- * zero payload bytes (the reference emits what its decoder left in pkt->payload).
+ * _set_modulation.  Host formatting only.  The reference logs pkt->payload even where the payload
+ * decode failed (rv < 2): records produced with BTBB_B200_MODE_FLAG_RAW_PAYLOAD carry those bytes and
+ * give byte-identical files for EVERY packet; without the flag such packets get zero payload bytes.
  */
 typedef struct btbb_b200_pcap_meta {
 	uint64_t ns;          /* timestamp, nanoseconds */
@@ -330,6 +362,13 @@ int64_t btbb_b200_pcap_file_header(uint8_t *out, int64_t cap);
 int64_t btbb_b200_pcap_bredr_records(const btbb_b200_hit *hits, const btbb_b200_decoded *dec,
 				     const btbb_b200_pcap_meta *meta, int64_t n,
 				     uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap);
+
+/* the same packets as pcapng enhanced packet blocks (btbb_pcapng_append_packet, pcapng-bt.c:176-264);
+ * pad bytes are zero (upstream leaves uninitialised stack bytes there).  Section header and interface
+ * description blocks are the capture program's to write. */
+int64_t btbb_b200_pcapng_bredr_blocks(const btbb_b200_hit *hits, const btbb_b200_decoded *dec,
+				      const btbb_b200_pcap_meta *meta, int64_t n,
+				      uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap);
 
 /* ---- synthetic capture generator (SURVEY.md 8d "Synthetic input"; test/bench data only) ---- */
 typedef struct btbb_b200_synth_cfg {

@@ -27,6 +27,11 @@ class PktIn(C.Structure):
                 ("whitened", C.c_uint8), ("type", C.c_uint8), ("pad", C.c_uint8), ("reserved", C.c_uint32)]
 
 
+class HopCfg(C.Structure):
+    _fields_ = [("address", C.c_uint32), ("afh", C.c_uint8), ("aliased", C.c_uint8), ("pad", C.c_uint8 * 2),
+                ("afh_map", C.c_uint8 * 10), ("pad2", C.c_uint8 * 2)]
+
+
 class SynthCfg(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_symbols", C.c_int64), ("first_symbol", C.c_int64),
                 ("stride", C.c_int32), ("n_laps", C.c_int32), ("ber_q32", C.c_uint32),
@@ -96,8 +101,11 @@ _PROTOS = {
     "btbb_b200_uap_sieve_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "btbb_b200_uap_sieve_host": (_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp]),
     "btbb_b200_group_by_lap": (_i64, [_vp, _i64, _vp, _vp, _vp]),
+    "btbb_b200_hop_sequence_dev": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "btbb_b200_hop_winnow": (_int, [_vp, _vp, _u32, _int, _vp, _vp, _vp, _i64, C.POINTER(_i64), _vp]),
     "btbb_b200_pcap_file_header": (_i64, [_vp, _i64]),
     "btbb_b200_pcap_bredr_records": (_i64, [_vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64]),
+    "btbb_b200_pcapng_bredr_blocks": (_i64, [_vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64]),
     "btbb_b200_synth_host": (_int, [C.POINTER(SynthCfg), _vp]),
     "btbb_b200_synth_dev": (_int, [C.POINTER(SynthCfg), _vp, _vp]),
     "btbb_b200_synth_planted": (_int, [C.POINTER(SynthCfg), _i64, C.POINTER(Planted)]),
@@ -192,6 +200,36 @@ def decode_smallcall(symbols, length, clkn=0, uap=0, whitened=1, ptype=0, mode=0
     out = np.zeros(64 if (mode & 0xff) == MODE_TRY_CLOCKS else 1, dtype=DECODED_DTYPE)
     check(lib().btbb_b200_decode_smallcall(symbols.ctypes.data, length, clkn, uap, whitened, ptype, mode, out.ctypes.data))
     return out
+
+
+def hop_cfg(address, afh_map=None, aliased=False):
+    cfg = HopCfg(address=address & 0xFFFFFFF, afh=1 if afh_map else 0, aliased=1 if aliased else 0)
+    if afh_map:
+        for i, b in enumerate(bytes(afh_map)[:10]):
+            cfg.afh_map[i] = b
+    return cfg
+
+
+def hop_winnow(ctx, cfg, known6, indices, channels, max_candidates=1 << 21):
+    """btbb_b200_hop_winnow: (survivors ascending, survivors_after per observation)"""
+    idx = np.ascontiguousarray(indices, dtype=np.int32)
+    ch = np.ascontiguousarray(channels, dtype=np.uint8)
+    cands = np.zeros(max_candidates, dtype=np.uint32)
+    after = np.zeros(len(idx), dtype=np.int32)
+    n = _i64(0)
+    check(lib().btbb_b200_hop_winnow(ctx.h, C.byref(cfg), known6, len(idx), idx.ctypes.data, ch.ctypes.data, cands.ctypes.data,
+                                     max_candidates, C.byref(n), after.ctypes.data))
+    return cands[: n.value].copy(), after
+
+
+def pcapng_bredr_blocks(hits, dec, meta, reflap=LAP_ANY, refuap=0xFF):
+    """btbb_b200_pcapng_bredr_blocks: the enhanced packet blocks as bytes"""
+    L = lib()
+    need = L.btbb_b200_pcapng_bredr_blocks(hits.ctypes.data, dec.ctypes.data, meta.ctypes.data, len(hits), reflap, refuap, None, 0)
+    buf = np.zeros(max(need, 1), dtype=np.uint8)
+    assert L.btbb_b200_pcapng_bredr_blocks(hits.ctypes.data, dec.ctypes.data, meta.ctypes.data, len(hits), reflap, refuap,
+                                           buf.ctypes.data, need) == need
+    return buf[:need].tobytes()
 
 
 def synth_host(cfg):

@@ -21,6 +21,7 @@
  *            (cp.async.bulk shared -> global, 11 904 bytes), or the UAP sieve's 16-bit words.
  */
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 #include "bt_math.h"
 #include "decode_core.h"
@@ -55,8 +56,8 @@ struct dec_args {
 	const btd_tables *tables;
 };
 
-template <int OUT, int WARPS>
-constexpr int smem_bytes() { return SMALL_BYTES + NIB_BYTES + WARPS * (PKT_BYTES + (OUT == OUT_FULL64 ? STAGE_BYTES : 0)); }
+template <int OUT, int WARPS, int SREC>
+constexpr int smem_bytes() { return SMALL_BYTES + NIB_BYTES + WARPS * (PKT_BYTES + (OUT == OUT_FULL64 ? SREC * (int)sizeof(btbb_b200_decoded) : 0)); }
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p)
 {
@@ -93,7 +94,7 @@ __device__ __forceinline__ void ingest(btd_pkt &P, const uint4 *base, int sh, in
 }
 
 /* FEC 2/3 blocks [0, nblk) from symbol `start`: lane = block; returns the first uncorrectable one */
-__device__ __forceinline__ int fec_blocks(const btd_pkt &P, uint32_t *dst, int start, int nblk, const uint8_t *col, int lane)
+__device__ __noinline__ int fec_blocks(const btd_pkt &P, uint32_t *dst, int start, int nblk, const uint8_t *col, int lane)
 {
 	const int nwords = (10 * nblk + 31) / 32 + 1;
 	for (int w = lane; w < nwords; w += 32) dst[w] = 0;
@@ -118,7 +119,7 @@ __device__ __forceinline__ int fec_blocks(const btd_pkt &P, uint32_t *dst, int s
 }
 
 /* dp[L] = XOR of the CRC weights of the first L bytes of a source: lane = run of bytes, XOR scan over lanes */
-__device__ __forceinline__ void build_dp(const btd_pkt &P, const uint16_t *nib, int src, int nbytes, uint16_t *dp, int lane)
+__device__ __noinline__ void build_dp(const btd_pkt &P, const uint16_t *nib, int src, int nbytes, uint16_t *dp, int lane)
 {
 	if (nbytes <= 0) { if (lane == 0) dp[0] = 0; return; }
 	const int C = (nbytes + 31) >> 5;
@@ -196,7 +197,9 @@ __device__ __forceinline__ void evaluate(const btd_ctx &c, const btd_pkt &P, btd
 	btd_eval_end(P, s, kind, found);
 }
 
-template <int OUT, int WARPS>
+/* SREC = records staged per bulk store (OUT_FULL64): 32 = a whole round of clocks, 16 = half a round
+ * (half the staging memory per warp, twice the warps per SM) */
+template <int OUT, int WARPS, int SREC>
 __global__ void __launch_bounds__(WARPS * 32, OUT == OUT_FULL64 ? 1 : 3) decode_kernel(const dec_args a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -214,7 +217,8 @@ __global__ void __launch_bounds__(WARPS * 32, OUT == OUT_FULL64 ? 1 : 3) decode_
 
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	btd_pkt &P = *reinterpret_cast<btd_pkt *>(smem + SMALL_BYTES + NIB_BYTES + wid * PKT_BYTES);
-	uint32_t *stage = reinterpret_cast<uint32_t *>(smem + SMALL_BYTES + NIB_BYTES + WARPS * PKT_BYTES + wid * STAGE_BYTES);
+	constexpr int STG_BYTES = SREC * (int)sizeof(btbb_b200_decoded);
+	uint32_t *stage = reinterpret_cast<uint32_t *>(smem + SMALL_BYTES + NIB_BYTES + WARPS * PKT_BYTES + wid * STG_BYTES);
 	if (lane == 0) P.raw[BTD_RAW_WORDS - 1] = 0;
 	btd_ctx c;
 	c.s = s_small; c.nib = s_nib; c.wp = a.tables->wp;
@@ -265,10 +269,13 @@ __global__ void __launch_bounds__(WARPS * 32, OUT == OUT_FULL64 ? 1 : 3) decode_
 				type_mask = 1u << s.type;
 			}
 		} else {
-			btd_lane t0, t1;
-			btd_lane_init(t0, lane); btd_lane_init(t1, lane + 32);
-			btd_try_clock(c, P, t0); btd_try_clock(c, P, t1);
-			type_mask = __reduce_or_sync(FULL, (1u << t0.type) | (1u << t1.type));
+			/* packet type under clock candidates lane and lane + 32 (try_clock's type field alone) */
+			uint32_t ty0 = 0, ty1 = 0;
+			if (hdr_ok) {
+				ty0 = ((hdr ^ btd_white(c, lane, 0, 18)) >> 3) & 15u;
+				ty1 = ((hdr ^ btd_white(c, lane + 32, 0, 18)) >> 3) & 15u;
+			}
+			type_mask = __reduce_or_sync(FULL, (1u << ty0) | (1u << ty1));
 		}
 		btd_needs nd;
 		btd_needs_for(type_mask, length, 0, &nd);
@@ -340,56 +347,61 @@ __global__ void __launch_bounds__(WARPS * 32, OUT == OUT_FULL64 ? 1 : 3) decode_
 				if (OUT == OUT_TC16) {
 					a.tc16[p * 64 + s.clock] = (uint16_t)btd_tc16(s);
 				} else {
-					/* the previous bulk store has to be done reading the staging buffer */
-					if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-					__syncwarp();
-					{
-						uint4 *z = reinterpret_cast<uint4 *>(stage);
-						for (int i = lane; i < STAGE_BYTES / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-					}
-					__syncwarp();
-					uint32_t *rec = stage + lane * REC_WORDS;      /* 93 words apart: conflict-free */
-					#pragma unroll
-					for (int w = 0; w < 7; w++) rec[w] = btd_record_word(s, (int)hdr_ok, 0, w);
-					/* payload: only the words that carry bits; the bit source is a pointer, a start bit and a
-					 * stride, so every lane runs the same instructions whatever its packet type is */
-					const int nbits = btd_emit_bits(s, a.raw_payload);
-					if (nbits > 0) {
-						const int nw = (nbits + 31) >> 5;
-						int q = btd_q18(c, s.pay_clk);
-						const uint32_t *sb;
-						int pos, step;
-						btd_src_desc(P, s.src, &sb, &pos, &step);
-						const uint32_t sh32 = (uint32_t)pos & 31u, adv = (uint32_t)step >> 5;
-						const uint32_t *wp = sb + (pos >> 5);
-						uint32_t lo_w = wp[0];
-						for (int j = 0; j < nw; j++) {
-							const uint32_t hi_w = wp[1];
-							uint32_t d = __funnelshift_r(lo_w, hi_w, sh32);
-							if (c.whitened) d ^= s_small->wrot[q];
-							if (j == nw - 1 && (nbits & 31)) d &= (1u << (nbits & 31)) - 1u;
-							rec[7 + j] = d;
-							if (adv) lo_w = hi_w;
-							wp += adv;
-							q += 32; if (q >= 127) q -= 127;
-						}
-					}
-					unsigned char *dst = reinterpret_cast<unsigned char *>(&a.out[p * 64 + 32 * round]);
-					if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+					#pragma unroll 1
+					for (int part = 0; part < 32 / SREC; part++) {
+						/* the previous bulk store has to be done reading the staging buffer */
+						if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 						__syncwarp();
-						if (lane == 0) {
-							const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
-							asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-								     :: "l"(dst), "r"(src), "r"(STAGE_BYTES) : "memory");
-							asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+						{
+							uint4 *z = reinterpret_cast<uint4 *>(stage);
+							for (int i = lane; i < STG_BYTES / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
 						}
-					} else {
 						__syncwarp();
-						uint32_t *o = reinterpret_cast<uint32_t *>(dst);
-						for (int w = lane; w < 32 * REC_WORDS; w += 32) o[w] = stage[w];
+						if (SREC == 32 || (lane / SREC) == part) {
+							uint32_t *rec = stage + (lane % SREC) * REC_WORDS;      /* 93 words apart: conflict-free */
+							#pragma unroll
+							for (int w = 0; w < 7; w++) rec[w] = btd_record_word(s, (int)hdr_ok, 0, w);
+							/* payload: only the words that carry bits; the bit source is a pointer, a start bit and
+							 * a stride, so every lane runs the same instructions whatever its packet type is */
+							const int nbits = btd_emit_bits(s, a.raw_payload);
+							if (nbits > 0) {
+								const int nw = (nbits + 31) >> 5;
+								int q = btd_q18(c, s.pay_clk);
+								const uint32_t *sb;
+								int pos, step;
+								btd_src_desc(P, s.src, &sb, &pos, &step);
+								const uint32_t sh32 = (uint32_t)pos & 31u, adv = (uint32_t)step >> 5;
+								const uint32_t *wp = sb + (pos >> 5);
+								uint32_t lo_w = wp[0];
+								for (int j = 0; j < nw; j++) {
+									const uint32_t hi_w = wp[1];
+									uint32_t d = __funnelshift_r(lo_w, hi_w, sh32);
+									if (c.whitened) d ^= s_small->wrot[q];
+									if (j == nw - 1 && (nbits & 31)) d &= (1u << (nbits & 31)) - 1u;
+									rec[7 + j] = d;
+									if (adv) lo_w = hi_w;
+									wp += adv;
+									q += 32; if (q >= 127) q -= 127;
+								}
+							}
+						}
+						unsigned char *dst = reinterpret_cast<unsigned char *>(&a.out[p * 64 + 32 * round + SREC * part]);
+						if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+							asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+							__syncwarp();
+							if (lane == 0) {
+								const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+								asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+									     :: "l"(dst), "r"(src), "r"(STG_BYTES) : "memory");
+								asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+							}
+						} else {
+							__syncwarp();
+							uint32_t *o = reinterpret_cast<uint32_t *>(dst);
+							for (int w = lane; w < SREC * REC_WORDS; w += 32) o[w] = stage[w];
+						}
+						__syncwarp();
 					}
-					__syncwarp();
 				}
 			}
 		}
@@ -431,11 +443,11 @@ int ensure_dec_tables(btbb_b200_ctx *ctx)
 	return BTBB_B200_OK;
 }
 
-template <int OUT, int WARPS>
+template <int OUT, int WARPS, int SREC = 32>
 int launch(btbb_b200_ctx *ctx, const dec_args &a, int64_t n_max, cudaStream_t st)
 {
-	auto kern = decode_kernel<OUT, WARPS>;
-	constexpr int smem = smem_bytes<OUT, WARPS>();
+	auto kern = decode_kernel<OUT, WARPS, SREC>;
+	constexpr int smem = smem_bytes<OUT, WARPS, SREC>();
 	static bool configured[16];
 	const int dev = ctx->device;
 	if (dev < 0 || dev >= 16 || !configured[dev]) {
@@ -477,8 +489,11 @@ extern "C" int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream,
 	a.raw_payload = (mode & BTBB_B200_MODE_FLAG_RAW_PAYLOAD) != 0;
 	a.mode = mode & ~BTBB_B200_MODE_FLAG_RAW_PAYLOAD;
 	a.out = d_out; a.tables = static_cast<const btd_tables *>(ctx->d_dec_tables);
-	if (a.mode == BTBB_B200_MODE_TRY_CLOCKS)
-		return launch<OUT_FULL64, 12>(ctx, a, n, (cudaStream_t)cuda_stream);
+	if (a.mode == BTBB_B200_MODE_TRY_CLOCKS) {
+		const char *e = getenv("BTBB_B200_DECODE_CFG");      /* developer A/B */
+		if (e && !strcmp(e, "full12")) return launch<OUT_FULL64, 12, 32>(ctx, a, n, (cudaStream_t)cuda_stream);
+		return launch<OUT_FULL64, 24, 16>(ctx, a, n, (cudaStream_t)cuda_stream);
+	}
 	return launch<OUT_ONE, 8>(ctx, a, n, (cudaStream_t)cuda_stream);
 }
 

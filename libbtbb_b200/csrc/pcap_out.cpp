@@ -5,9 +5,13 @@
  * of from a btbb_packet.  Pure host formatting, little-endian on the wire as in
  * pcap-common.h:84-97 (DLT 255, LINKTYPE_BLUETOOTH_BREDR_BB).
  *
- * Known gap: for a packet whose payload decode FAILED (rv < 2) the reference still emits the
- * pkt->payload bytes its decoder left behind, while btbb_b200_decoded carries payload bytes only
- * for rv >= 2; such a record comes out with the right length and zero payload bytes.
+ * btbb_b200_pcapng_bredr_blocks writes the same packets as pcapng enhanced packet blocks
+ * (btbb_pcapng_append_packet, pcapng-bt.c:176-264).
+ *
+ * For a packet whose payload decode FAILED (rv < 2) the reference still logs the pkt->payload bytes
+ * its decoder left behind: ask the decode entry points for records with
+ * BTBB_B200_MODE_FLAG_RAW_PAYLOAD and the files are byte-identical for every packet; without the
+ * flag such a record comes out with the right length and zero payload bytes.
  */
 #include <string.h>
 #include <algorithm>
@@ -78,6 +82,55 @@ extern "C" int64_t btbb_b200_pcap_bredr_records(const btbb_b200_hit *hits, const
 		/* btbb_get_payload_packed: payload_length bytes; the record carries 344, the rest is zero */
 		for (int64_t j = 0; j < caplen; j++) p[j] = j < 344 ? dec[i].payload[j] : 0;
 		p += caplen;
+	}
+	return need;
+}
+
+/* n enhanced packet blocks of btbb_pcapng_append_packet (pcapng-bt.c:176-264; block layout
+ * pcapng.h, BR/EDR header pcap-common.h:84-97): block type 6, interface 0, the timestamp in
+ * nanoseconds split high / low, captured = packet length = 22 + payload bytes, data padded to four
+ * bytes (pad bytes are ZERO here; upstream leaves whatever its stack held), a zero "no options" word
+ * and the trailing block length.  Same size-query convention as btbb_b200_pcap_bredr_records.  The
+ * section header / interface description blocks are the capture program's to write. */
+extern "C" int64_t btbb_b200_pcapng_bredr_blocks(const btbb_b200_hit *hits, const btbb_b200_decoded *dec,
+						 const btbb_b200_pcap_meta *meta, int64_t n,
+						 uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap)
+{
+	if (n < 0 || (n > 0 && (!hits || !dec || !meta))) return -1;
+	int64_t need = 0;
+	for (int64_t i = 0; i < n; i++) {
+		int64_t len = dec[i].payload_length;
+		if (len < 0) len = 0;
+		if (len > (int64_t)MAX_PAYLOAD) len = MAX_PAYLOAD;
+		need += 4 * ((36 + BB_HEADER + len + 3) / 4);
+	}
+	if (!out || need > cap) return need;
+	uint8_t *p = out;
+	for (int64_t i = 0; i < n; i++) {
+		const btbb_b200_pcap_meta &m = meta[i];
+		int64_t caplen = dec[i].payload_length;
+		if (caplen < 0) caplen = 0;
+		if (caplen > (int64_t)MAX_PAYLOAD) caplen = MAX_PAYLOAD;
+		const uint32_t plen = (uint32_t)(BB_HEADER + caplen), blen = 4 * ((36 + plen + 3) / 4);
+		uint16_t flags = F_DEWHITENED | F_SIGPOWER_VALID;
+		if (m.noisedbm < m.sigdbm) flags |= F_NOISEPOWER_VALID;
+		if (reflap != BTBB_B200_LAP_ANY) flags |= F_REFLAP_VALID;
+		if (refuap != 0xff) flags |= F_REFUAP_VALID;
+		if (caplen) flags |= F_PAYLOAD_PRESENT;
+		memset(p, 0, blen);
+		le32(p, 6); le32(p + 4, blen); le32(p + 8, 0);
+		le32(p + 12, (uint32_t)(m.ns >> 32)); le32(p + 16, (uint32_t)m.ns);
+		le32(p + 20, plen); le32(p + 24, plen);
+		uint8_t *b = p + 28;
+		b[0] = m.channel; b[1] = (uint8_t)m.sigdbm; b[2] = (uint8_t)m.noisedbm; b[3] = hits[i].ac_errors;
+		b[4] = (uint8_t)((m.transport << 4) | m.modulation);
+		le32(b + 8, hits[i].lap);
+		le32(b + 12, (reflap & 0xffffffu) | ((uint32_t)refuap << 24));
+		le32(b + 16, dec[i].header_packed);
+		le16(b + 20, flags);
+		for (int64_t j = 0; j < caplen; j++) b[BB_HEADER + j] = j < 344 ? dec[i].payload[j] : 0;
+		le32(p + blen - 4, blen);
+		p += blen;
 	}
 	return need;
 }

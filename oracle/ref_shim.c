@@ -315,6 +315,36 @@ int ref_pcap_bredr(const char *path, char *stream, int64_t stream_length, const 
 	return 0;
 }
 
+/* the same through the reference's pcapng writer (pcapng-bt.c:134-264) */
+int ref_pcapng_bredr(const char *path, char *stream, int64_t stream_length, const ref_hit *hits, const ref_pkt_in *pkts,
+		   const ref_pcap_meta *meta, int64_t n, uint32_t reflap, uint8_t refuap, int32_t *rv)
+{
+	btbb_pcapng_handle *h = NULL;
+	int64_t i;
+	static char zero[1];
+	if (btbb_pcapng_create_file(path, "b200 parity", &h)) return -1;
+	for (i = 0; i < n; i++) {
+		btbb_packet *p = btbb_packet_new();
+		int length = pkts[i].length > 3125 ? 3125 : pkts[i].length, ok, r = -1;
+		if (pkts[i].offset < 0 || pkts[i].offset >= stream_length) length = 0;
+		else if (pkts[i].offset + length > stream_length) length = (int)(stream_length - pkts[i].offset);
+		p->LAP = hits[i].lap; p->ac_errors = hits[i].ac_errors; p->flags = 0;
+		btbb_packet_set_flag(p, BTBB_WHITENED, pkts[i].whitened);
+		btbb_packet_set_data(p, length > 0 ? stream + pkts[i].offset : zero, length, meta[i].channel, pkts[i].clkn << 1);
+		btbb_packet_set_uap(p, pkts[i].uap);
+		btbb_packet_set_flag(p, BTBB_CLK6_VALID, 1);
+		btbb_packet_set_transport(p, meta[i].transport);
+		btbb_packet_set_modulation(p, meta[i].modulation);
+		ok = btbb_decode_header(p);
+		if (ok) r = btbb_decode_payload(p);
+		if (rv) rv[i] = r;
+		btbb_pcapng_append_packet(h, meta[i].ns, meta[i].sigdbm, meta[i].noisedbm, reflap, refuap, p);
+		btbb_packet_unref(p);
+	}
+	btbb_pcapng_close(h);
+	return 0;
+}
+
 /* ---- hop sequence: the reference's gen_hop_pattern (bluetooth_piconet.c:365-377) for one address,
  * entries [first, first + n) of its 2^27-entry table copied out.  afh_map == NULL: all channels. ---- */
 void ref_hop_sequence(uint32_t address, const uint8_t *afh_map, int64_t first, int64_t n, uint8_t *out)
@@ -340,3 +370,45 @@ void ref_hop_sequence(uint32_t address, const uint8_t *afh_map, int64_t first, i
 	btbb_piconet_unref(pn);
 }
 
+
+/* ---- hop reversal: the reference's own btbb_init_hop_reversal (bluetooth_piconet.c:475-499) and
+ * btbb_winnow (:613-645) on a piconet whose pattern log holds the given observations, one more per
+ * call.  counts[j] = pn->num_candidates after observation j (-1 once the reference has stopped: it
+ * breaks at <= 1 candidates).  cands receives the surviving CLK1-27 values.  Returns the final count. ---- */
+int ref_hop_winnow(uint32_t address, const uint8_t *afh_map, int aliased, uint32_t known6, int n_obs,
+		   const int32_t *indices, const uint8_t *channels, int32_t *counts, uint32_t *cands, int max)
+{
+	btbb_piconet *pn = btbb_piconet_new();
+	int i, j, saved, devnull, n = 0;
+	pn->LAP = address & 0xffffff;
+	pn->UAP = (address >> 24) & 0xff;
+	if (afh_map) {
+		btbb_piconet_set_flag(pn, BTBB_IS_AFH, 1);
+		for (i = 0; i < 10; i++) pn->afh_map[i] = afh_map[i];
+		pn->used_channels = 0;
+		for (i = 0; i < 79; i++) pn->used_channels += (afh_map[i / 8] >> (i % 8)) & 1;
+	} else
+		pn->used_channels = 79;
+	pn->clk_offset = (int)(known6 & 0x3f);
+	pn->first_pkt_time = 0;
+	for (j = 0; j < n_obs && j < MAX_PATTERN_LENGTH; j++) {
+		pn->pattern_indices[j] = indices[j];
+		pn->pattern_channels[j] = channels[j];
+		counts[j] = -1;
+	}
+	fflush(stdout);
+	saved = dup(1); devnull = open("/dev/null", O_WRONLY); dup2(devnull, 1);
+	pn->packets_observed = 1;
+	btbb_init_hop_reversal(aliased, pn);
+	for (j = 0; j < n_obs; j++) {
+		pn->packets_observed = j + 1;
+		n = btbb_winnow(pn);
+		counts[j] = n;
+		if (n <= 1) break;
+	}
+	fflush(stdout);
+	dup2(saved, 1); close(saved); close(devnull);
+	if (n >= 1 && btbb_piconet_get_flag(pn, BTBB_HOP_REVERSAL_INIT))
+		for (i = 0; i < n && i < max; i++) cands[i] = pn->clock_candidates[i];
+	return n;
+}

@@ -221,7 +221,24 @@ def gen_chain79():
     raw = np.array([util.decode_one_raw(R, "ref", s, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"])) for p in dec])
     tc = np.array([util.try_clock_one(R, "ref", s, int(p["offset"]), int(p["length"]), c) for p in dec for c in range(64)])
     st, rv = util.sieve_run(R, "ref", s, sv, gs)
-    out = {"blocks": 6, "symbols": n, "hits": len(hits), "hits_sha256": util.digest(hits), "decode_sha256": util.digest(recs),
+    # the capture files the reference writes for these packets (pcap whole; pcapng: its enhanced packet blocks, pad bytes zeroed)
+    import hashlib
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import test_pcap
+    meta = util.chain79_meta(dec)
+    R.ref_pcap_bredr.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint8, C.c_void_p]
+    R.ref_pcapng_bredr.argtypes = R.ref_pcap_bredr.argtypes
+    files = {}
+    for kind, fn in (("pcap", R.ref_pcap_bredr), ("pcapng", R.ref_pcapng_bredr)):
+        path = os.path.join("/tmp", f"golden_chain_{os.getpid()}.{kind}").encode()
+        rvv = np.zeros(len(hits), dtype=np.int32)
+        assert fn(path, s.ctypes.data, len(s), hits.ctypes.data, dec.ctypes.data, meta.ctypes.data, len(hits), B.LAP_ANY, 0xFF, rvv.ctypes.data) == 0
+        files[kind] = open(path.decode(), "rb").read()
+        os.remove(path.decode())
+    png = test_pcap._epbs(files["pcapng"])
+    out = {"pcap": [len(files["pcap"]), hashlib.sha256(files["pcap"]).hexdigest()],
+           "pcapng_blocks": [len(png), hashlib.sha256(png).hexdigest()],
+           "blocks": 6, "symbols": n, "hits": len(hits), "hits_sha256": util.digest(hits), "decode_sha256": util.digest(recs),
            "decode_raw_sha256": util.digest(raw), "try_clocks_sha256": util.digest(tc),
            "rv_hist": {str(k): int(v) for k, v in zip(*np.unique(recs["rv"], return_counts=True))},
            "piconets": len(gs) - 1, "piconets_resolved": int(((st["flags"] >> 2) & 1).sum()),

@@ -80,3 +80,33 @@ def test_chain_on_79_channel_capture(gpu_ctx2, orc, product_lib):
     for gi, lap in enumerate(laps):
         p = next(B.planted(cfg, int(q["offset"]) // util.CHAIN_BLK) for q in sv[gs[gi]:gs[gi + 1]])
         assert st[gi]["uap"] == p.uap
+
+
+def test_gpu_records_to_pcap_files(gpu_ctx2, orc, product_lib, tmp_path):
+    """GPU hits + GPU decode records (raw-payload flag) -> btbb_b200_pcap_bredr_records /
+    btbb_b200_pcapng_bredr_blocks == the files the reference writes for the same capture, EVERY packet
+    included; digests from the reference in tests/golden/chain79.json."""
+    import hashlib
+    import torch
+    import test_pcap
+    g = json.load(open(os.path.join(util.GOLDEN, "chain79.json")))
+    cfg, s, n = util.chain79_case(g["blocks"])
+    d = torch.from_numpy(s).cuda()
+    cap = 4096
+    d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    cnt, rc = gpu_ctx2.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=B.LAP_ANY, k=2)
+    hits = d_hits[:cnt].cpu().numpy().reshape(-1).view(B.HIT_DTYPE)
+    dec, sv, gs, laps = util.chain79_packets(cfg, hits)
+    d_pk = torch.from_numpy(dec.view(np.uint8)).cuda()
+    d_out = torch.zeros((cnt, 372), dtype=torch.uint8, device="cuda")
+    B.check(product_lib.btbb_b200_decode_dev(gpu_ctx2.h, d.data_ptr(), n + 63, d_pk.data_ptr(), cnt,
+                                             B.MODE_DECODE | B.MODE_FLAG_RAW_PAYLOAD, d_out.data_ptr(), 0))
+    torch.cuda.synchronize()
+    recs = d_out.cpu().numpy().reshape(-1).view(B.DECODED_DTYPE)
+    meta = util.chain79_meta(dec)
+    pcap = B.pcap_bredr(hits, recs, meta)
+    png = B.pcapng_bredr_blocks(hits, recs, meta)
+    assert [len(pcap), hashlib.sha256(pcap).hexdigest()] == g["pcap"]
+    assert [len(png), hashlib.sha256(png).hexdigest()] == g["pcapng_blocks"]
+    if util.have_ref():
+        assert pcap == test_pcap._ref_pcap(tmp_path, s, hits, dec, meta)

@@ -37,3 +37,28 @@ def test_oracle_hop_sequence_windows(name):
             assert np.array_equal(got, ref_full[first:first + n])
     if ref_full is not None:
         assert hashlib.sha256(ref_full.tobytes()).hexdigest() == fx["full"]
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="compiled reference not built here")
+def test_reference_winnow_agrees_with_a_filter_over_its_table():
+    """The harness tests/test_gpu_hops.py leans on: the reference's btbb_init_hop_reversal + btbb_winnow
+    (oracle/ref_shim.c:ref_hop_winnow) give the candidate counts a plain filter over the sequence gives."""
+    import ctypes as C
+    R = util.ref()
+    R.ref_hop_winnow.argtypes = [C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    address, afh = CASES["a96ef25"]
+    full = _seq(util.oracle(), "orc", address, afh, 0, 1 << 27)
+    mask = (1 << 27) - 1
+    true_clk = 0x2345678
+    idx = np.array([0, 7, 9, 30, 31, 60, 100], dtype=np.int32)
+    ch = np.ascontiguousarray(full[(true_clk + idx) & mask])
+    counts = np.zeros(len(idx), dtype=np.int32)
+    rc = np.zeros(1 << 16, dtype=np.uint32)
+    n = R.ref_hop_winnow(address, None, 0, true_clk & 63, len(idx), idx.ctypes.data, ch.ctypes.data, counts.ctypes.data, rc.ctypes.data, len(rc))
+    want = np.arange(true_clk & 63, 1 << 27, 64, dtype=np.int64)
+    traj = []
+    for j in range(len(idx)):
+        want = want[full[(want + int(idx[j])) & mask] == ch[j]]
+        traj.append(len(want))
+    stop = next(j for j, v in enumerate(traj) if v <= 1)
+    assert counts[:stop + 1].tolist() == traj[:stop + 1] and n == 1 and rc[0] == true_clk

@@ -249,3 +249,13 @@ def test_chain79_fixture(orc):
         sym = np.ascontiguousarray(s[int(p["offset"]):int(p["offset"]) + int(p["length"])])
         assert B.decode_smallcall(sym, len(sym), int(p["clkn"]), int(p["uap"]))[0].tobytes() == recs[i].tobytes()
         assert B.decode_smallcall(sym, len(sym), mode=B.MODE_TRY_CLOCKS).tobytes() == tc[64 * i:64 * i + 64].tobytes()
+    # capture files from the product's host path: records with the raw-payload flag -> the reference's pcap file
+    # and pcapng packet blocks, every packet included
+    import hashlib
+    small = np.array([B.decode_smallcall(np.ascontiguousarray(s[int(p["offset"]):int(p["offset"]) + int(p["length"])]), int(p["length"]),
+                                         int(p["clkn"]), int(p["uap"]), mode=B.MODE_FLAG_RAW_PAYLOAD)[0] for p in dec])
+    assert small.tobytes() == raw.tobytes()
+    meta = util.chain79_meta(dec)
+    pcap, png = B.pcap_bredr(hits, small, meta), B.pcapng_bredr_blocks(hits, small, meta)
+    assert [len(pcap), hashlib.sha256(pcap).hexdigest()] == g["pcap"]
+    assert [len(png), hashlib.sha256(png).hexdigest()] == g["pcapng_blocks"]

@@ -113,3 +113,43 @@ def test_raw_payload_semantics_and_full_file_parity(ber, seed, tmp_path):
     assert raw.tobytes() == ref_raw.tobytes()
     assert ((raw["rv"] < 2) & (raw["payload_length"] > 0)).sum() > 0        # the case in question occurs
     assert B.pcap_bredr(hits, raw, meta) == _ref_pcap(tmp_path, stream, hits, pkts, meta)
+
+
+def _epbs(data):
+    """the enhanced packet blocks of a pcapng file, pad bytes zeroed (upstream leaves stack garbage there)"""
+    out, at = bytearray(), 0
+    while at + 12 <= len(data):
+        btype = int.from_bytes(data[at:at + 4], "little")
+        blen = int.from_bytes(data[at + 4:at + 8], "little")
+        if blen < 12 or at + blen > len(data):
+            break
+        if btype == 6:
+            blk = bytearray(data[at:at + blen])
+            cap = int.from_bytes(blk[20:24], "little")
+            for i in range(28 + cap, blen - 8):
+                blk[i] = 0
+            out += blk
+        at += blen
+    return bytes(out)
+
+
+@pytest.mark.parametrize("ber,seed", [(0.0, 5), (0.01, 7)])
+def test_pcapng_blocks_match_reference(ber, seed, tmp_path):
+    """btbb_b200_pcapng_bredr_blocks == the enhanced packet blocks btbb_pcapng_append_packet writes
+    (pcapng-bt.c:176-264), for every packet when the records carry the raw payload bytes."""
+    if not util.have_ref():
+        pytest.skip("needs oracle/_ref (the compiled reference)")
+    O, R = util.oracle(), util.ref()
+    stream, hits, pkts, meta = build_case(ber=ber, seed=seed)
+    raw = np.array([util.decode_one_raw(O, "orc", stream, int(p["offset"]), int(p["length"]), int(p["clkn"]), int(p["uap"]))
+                    for p in pkts])
+    R.ref_pcapng_bredr.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_uint32, C.c_uint8, C.c_void_p]
+    for reflap, refuap in ((B.LAP_ANY, 0xFF), (0x9E8B33, 0x42)):
+        path = str(tmp_path / f"ref_{reflap:x}.pcapng").encode()
+        rv = np.zeros(len(hits), dtype=np.int32)
+        assert R.ref_pcapng_bredr(path, stream.ctypes.data, len(stream), hits.ctypes.data, pkts.ctypes.data, meta.ctypes.data,
+                                  len(hits), reflap, refuap, rv.ctypes.data) == 0
+        want = _epbs(open(path.decode(), "rb").read())
+        got = B.pcapng_bredr_blocks(hits, raw, meta, reflap, refuap)
+        assert len(want) > 36 * len(hits) and got == want

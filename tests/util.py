@@ -306,3 +306,13 @@ def chain79_packets(cfg, hits):
     sv["clkn"] = sv["offset"] // CHAIN_BLK
     sv["uap"] = 0
     return dec, sv, gs, laps
+
+
+def chain79_meta(dec):
+    """capture metadata for the pcap writers: 625 us slots, channel from the packet record"""
+    meta = np.zeros(len(dec), dtype=B.PCAP_META_DTYPE)
+    for i, p in enumerate(dec):
+        meta[i]["ns"] = 1_700_000_000_000_000_000 + 625_000 * (int(p["offset"]) // CHAIN_BLK)
+        meta[i]["sigdbm"], meta[i]["noisedbm"] = -30 - i % 40, -95 + i % 7
+        meta[i]["channel"], meta[i]["transport"], meta[i]["modulation"] = int(p["reserved"]) & 0xff, 1, 0
+    return meta
