@@ -126,6 +126,15 @@ int btbb_b200_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits);
  * straight from the kernels. */
 int btbb_b200_set_offset_bias(btbb_b200_ctx *ctx, int64_t bias);
 
+/* Tunables of one context (defaults in brackets); nothing here changes a result. */
+#define BTBB_B200_OPT_TILE_KERNEL_ONLY    1   /* [0] scans skip the bulk kernels and run the tile kernels (A/B check) */
+#define BTBB_B200_OPT_HOST_BYTE_ROUTE     2   /* [0] btbb_b200_find_ac_host copies the byte stream instead of packing on the host */
+#define BTBB_B200_OPT_HOST_SPLIT_PERMILLE 3   /* [0] share of a large host call that travels as bytes while the rest is packed */
+#define BTBB_B200_OPT_PACK_THREADS        4   /* [0 = all usable CPUs, at most 32] host pack threads */
+#define BTBB_B200_OPT_TRACE               5   /* [0] timing lines of the host-buffer scan on stderr */
+#define BTBB_B200_OPT_DECODE_WIDE_STAGING 6   /* [0] 64-clock sweep: 12 warps per SM staging 32 records instead of 24 x 16 */
+int btbb_b200_set_option(btbb_b200_ctx *ctx, int option, int64_t value);
+
 /* Measurement hook (bench.py's roofline): with profiling on, every scan records CUDA events right
  * before and after its bulk kernel on the scan's own stream; after the scan has been waited for,
  * btbb_b200_last_scan_kernel_ms returns that kernel's duration.  Off by default. */

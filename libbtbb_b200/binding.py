@@ -77,6 +77,7 @@ _PROTOS = {
     "btbb_b200_find_ac_dev_begin": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, _vp]),
     "btbb_b200_find_ac_dev_end": (_int, [_vp, C.POINTER(_i64)]),
     "btbb_b200_set_offset_bias": (_int, [_vp, _i64]),
+    "btbb_b200_set_option": (_int, [_vp, _int, _i64]),
     "btbb_b200_set_profiling": (_int, [_vp, _int]),
     "btbb_b200_last_scan_kernel_ms": (_int, [_vp, C.POINTER(C.c_float)]),
     "btbb_b200_find_ac_packed_dev": (_int, [_vp, _vp, _i64, _u32, _int, _vp, _i64, C.POINTER(_i64), _vp]),
@@ -191,6 +192,7 @@ def pcap_bredr(hits, dec, meta, reflap=LAP_ANY, refuap=0xFF):
     return buf.tobytes()
 
 
+OPT_TILE_KERNEL_ONLY, OPT_HOST_BYTE_ROUTE, OPT_HOST_SPLIT_PERMILLE, OPT_PACK_THREADS, OPT_TRACE, OPT_DECODE_WIDE_STAGING = 1, 2, 3, 4, 5, 6
 MODE_DECODE, MODE_TRY_CLOCKS, MODE_PAYLOAD, MODE_CRC_CHECK, MODE_RAW, MODE_FLAG_RAW_PAYLOAD = 0, 1, 2, 3, 16, 0x100
 
 
@@ -277,6 +279,9 @@ class Context:
                                          C.byref(n), stream)
         check(rc, allow=(-4,))
         return n.value, rc
+
+    def set_option(self, option, value):
+        check(lib().btbb_b200_set_option(self.h, option, value))
 
     def set_profiling(self, on=True):
         check(lib().btbb_b200_set_profiling(self.h, 1 if on else 0))

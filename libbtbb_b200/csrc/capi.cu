@@ -269,14 +269,14 @@ static int usable_cpus()
 	return n;
 }
 
-/* pack workers: every usable CPU up to 32 (BTBB_B200_PACK_THREADS overrides).  Measured on
+/* pack workers: every usable CPU up to 32 (BTBB_B200_OPT_PACK_THREADS overrides).  Measured on
  * the B200 host (2 x 32 cores, 16-CPU quota): ~5 GB/s of symbols per thread, and threads
  * beyond the quota only add throttling stalls at the per-chunk barriers. */
-static int pack_threads()
+static int pack_threads(const btbb_b200_ctx *ctx)
 {
 	int nt = usable_cpus();
 	if (nt > 32) nt = 32;
-	if (const char *e = getenv("BTBB_B200_PACK_THREADS")) nt = atoi(e);
+	if (ctx->opt_pack_threads > 0) nt = ctx->opt_pack_threads;
 	if (nt < 1) nt = 1;
 	if (nt > 128) nt = 128;
 	return nt;
@@ -312,7 +312,7 @@ static int pack_and_upload(btbb_b200_ctx *ctx, const char *stream, int64_t nsym)
 	job.chunk_words = chunk_words; job.total_words = total_words;
 	job.nchunks = (total_words + chunk_words - 1) / chunk_words;
 	job.stage[0] = ctx->h_pack[0]; job.stage[1] = ctx->h_pack[1];
-	int nt = pack_threads();
+	int nt = pack_threads(ctx);
 	if ((int64_t)nt > (chunk_words + 65535) / 65536) nt = (int)((chunk_words + 65535) / 65536);
 	job.ready.store(0);
 	std::vector<pthread_t> th((size_t)nt);
@@ -361,7 +361,7 @@ static double now_ms()
 
 /*
  * Large host-buffer call: the host cores pack the stream while it is copied, the packed bulk
- * kernels scan it.  Optionally (BTBB_B200_HOST_SPLIT=<fraction>) the head [0, split) travels
+ * kernels scan it.  Optionally (BTBB_B200_OPT_HOST_SPLIT_PERMILLE) the head [0, split) travels
  * in the byte format instead -- DMA straight from a pinned buffer, no CPU work, scanned chunk
  * by chunk as it arrives -- while the cores pack the rest.  On the B200 host this was
  * measured as no gain (profiles/README.md: DMA and pack threads compete for the same host
@@ -373,14 +373,11 @@ static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t sear
 			    int max_ac_errors, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits)
 {
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
-	const bool trace = getenv("BTBB_B200_TRACE") != NULL;
+	const bool trace = ctx->opt_trace != 0;
 	const double t0 = trace ? now_ms() : 0;
 	int64_t split = 0;
 	{
-		double frac = 0;
-		if (const char *e = getenv("BTBB_B200_HOST_SPLIT")) frac = atof(e);
-		if (frac < 0) frac = 0;
-		if (frac > 0.95) frac = 0.95;
+		const double frac = ctx->opt_host_split / 1000.0;
 		split = (int64_t)(frac * (double)search_length) & ~(int64_t)4095;
 	}
 	int rc;
@@ -430,7 +427,7 @@ static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t sear
 	if (trace)
 		fprintf(stderr, "[btbb_b200] find_ac_host: %lld symbols as bytes + %lld packed (%d threads): issue+pack %.2f ms, "
 			"byte part drained %.2f ms, packed scan+readback %.2f ms\n", (long long)split,
-			(long long)(search_length - split), pack_threads(), t1 - t0, t2 - t1, now_ms() - t2);
+			(long long)(search_length - split), pack_threads(ctx), t1 - t0, t2 - t1, now_ms() - t2);
 	if (overflow)
 		return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac_host: hit buffer too small");
 	return BTBB_B200_OK;
@@ -445,8 +442,7 @@ extern "C" int btbb_b200_find_ac_host(btbb_b200_ctx *ctx, const char *stream, in
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_host: bad arguments");
 	*n_hits = 0;
 	if (search_length == 0) return BTBB_B200_OK;
-	const char *env = getenv("BTBB_B200_HOST");      /* developer: "bytes" keeps the byte-format copy */
-	if (search_length >= ((int64_t)4 << 20) && !(env && !strcmp(env, "bytes")))
+	if (search_length >= ((int64_t)4 << 20) && !ctx->opt_host_bytes)      /* BTBB_B200_OPT_HOST_BYTE_ROUTE keeps the byte-format copy */
 		return scan_host_packed(ctx, stream, search_length, lap, max_ac_errors, hits, max_hits, n_hits);
 	return scan_host(ctx, stream, search_length, lap, max_ac_errors, hits, max_hits, n_hits, NULL);
 }

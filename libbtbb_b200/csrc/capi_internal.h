@@ -42,11 +42,6 @@ struct btbb_b200_ctx {
 	bt_scan_tables *d_tables;    /* device copy */
 	uint32_t *d_bloom;           /* bitmap over the low 32 syndrome bits of table entries (+ zero) */
 	int bloom_log2;              /* log2(bits) */
-	uint32_t *d_lut2;            /* bulk kernel: LUT A (codeword bits 32..44) then LUT B (bits 45..56) */
-	uint32_t *d_lut2b;           /* bulk kernel v4 (shipped): LUT A over codeword bits 34..46, LUT B over 47..56 */
-	uint32_t *d_lut3;            /* bulk kernel v4, LUTMODE 2: three field tables (8/8/7 bits of codeword bits 34..56) */
-	uint32_t *d_lut4;            /* bulk kernel v4: four field tables (7/6/6/6 bits of codeword bits 32..56) */
-	uint32_t *d_map2;            /* bulk kernel: 2^19-bit map of reachable low-32 syndromes, both tails (k <= 2) */
 	uint64_t cc[2];              /* 34-bit syndrome of PN ^ (legal tail << 57) */
 	uint32_t m32, m33;           /* parity masks over codeword bits 32..56 for syndrome bits 32 / 33 */
 	uint32_t m0;                 /* same for syndrome bit 0 */
@@ -97,6 +92,7 @@ struct btbb_b200_ctx {
 	void *d_scratch[4];          /* grow-only device scratch of the host-buffer entry points */
 	size_t scratch_cap[4];
 	cudaEvent_t ev_reset;        /* host-buffer scan: the counter reset has been enqueued */
+	int opt_tile_only, opt_host_bytes, opt_host_split, opt_pack_threads, opt_trace, opt_decode_wide;   /* btbb_b200_set_option */
 	cudaEvent_t prof_ev[2];      /* btbb_b200_set_profiling: around the bulk scan kernel */
 	int prof_on, prof_valid;
 	bt_shard *shard;             /* multi-GPU state (sharded.cu), NULL until btbb_b200_shard_init */

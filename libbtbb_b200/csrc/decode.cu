@@ -490,8 +490,8 @@ extern "C" int btbb_b200_decode_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream,
 	a.mode = mode & ~BTBB_B200_MODE_FLAG_RAW_PAYLOAD;
 	a.out = d_out; a.tables = static_cast<const btd_tables *>(ctx->d_dec_tables);
 	if (a.mode == BTBB_B200_MODE_TRY_CLOCKS) {
-		const char *e = getenv("BTBB_B200_DECODE_CFG");      /* developer A/B */
-		if (e && !strcmp(e, "full12")) return launch<OUT_FULL64, 12, 32>(ctx, a, n, (cudaStream_t)cuda_stream);
+		/* 24 warps per SM staging half a round of records each; BTBB_B200_OPT_DECODE_WIDE_STAGING: 12 warps, whole rounds */
+		if (ctx->opt_decode_wide) return launch<OUT_FULL64, 12, 32>(ctx, a, n, (cudaStream_t)cuda_stream);
 		return launch<OUT_FULL64, 24, 16>(ctx, a, n, (cudaStream_t)cuda_stream);
 	}
 	return launch<OUT_ONE, 8>(ctx, a, n, (cudaStream_t)cuda_stream);

@@ -386,8 +386,7 @@ __global__ void sort_scatter_kernel(const btbb_b200_hit *in, btbb_b200_hit *out,
 	}
 }
 
-#include "scan_v3.cuh"
-#include "scan_v4.cuh"
+#include "scan_common.cuh"
 #include "scan_v7.cuh"
 #include "scan_known.cuh"
 
@@ -477,10 +476,12 @@ static int unpack_to_bytes(btbb_b200_ctx *ctx, const uint32_t *d_words, int64_t 
 }
 
 /*
- * Dispatcher.  The promiscuous scan with tables for k <= 2 runs the warp-autonomous bulk
- * kernel (scan_v4.cuh; BTBB_B200_SCAN=v3 selects its predecessor) over every whole 4096-symbol strip that starts on a 32-byte
- * boundary; the unaligned head and the ragged tail go through the tile kernel above, as
- * do known-LAP scans and the larger error tables.  BTBB_B200_SCAN=v1 forces the tile kernel.
+ * Dispatcher.  Every whole 4096-symbol strip that starts on a 32-byte boundary goes through a bulk
+ * kernel -- scan_v7.cuh for promiscuous scans (its map hierarchy depends on the error tables the
+ * context was built with), scan_known.cuh for a known LAP; the unaligned head and the ragged tail go
+ * through the tile kernels above, as do known-LAP scans with k > 16 and streams shorter than a
+ * strip.  BTBB_B200_OPT_TILE_KERNEL_ONLY (btbb_b200_set_option) sends everything through the tile
+ * kernels (an A/B check the tests use).
  */
 int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
@@ -496,14 +497,11 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		      int64_t bias, cudaStream_t st, bt_slab_req *slab, int packed)
 {
 	if (slab) slab->used = 0;
-	const char *env = getenv("BTBB_B200_SCAN");
-	const bool force_v1 = env && !strcmp(env, "v1");
 	if (n <= 0) return BTBB_B200_OK;
 	const bool known = lap != BTBB_B200_LAP_ANY;
-	/* tables for 3 errors: only the byte-format v7 kernel has a bulk path (global second-level map) */
-	const bool k3 = !known && !ctx->d_map2 && ctx->d_map7g;      /* 3, 4 or 5 */
-	const bool k45 = k3 && ctx->table_k >= 4;
-	if ((!known && !ctx->d_map2 && !k3) || force_v1 || (known && k > 16) || (packed && n - 1 < v3::STRIP)) {
+	const bool k3 = !known && ctx->table_k >= 3;      /* second (3 errors) or first (4 / 5) map level in global memory */
+	const bool k45 = !known && ctx->table_k >= 4;
+	if (ctx->opt_tile_only || (known && k > 16) || (packed && n - 1 < sc::STRIP)) {
 		if (packed) {      /* no bulk kernel for this case: expand to the byte format and take the tile kernel */
 			int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), 0, n + 63, st);
 			if (rc0) return rc0;
@@ -511,23 +509,17 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		}
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
 	}
-	if (packed) env = NULL;      /* the developer switches below are for the byte format */
-	/* promiscuous default: scan_v7.cuh.  BTBB_B200_SCAN=v3 / v4a.. select the older generations,
-	 * v7 / v7f / .. the v7 variants (developer A/B runs, tools/kbench.py) */
-	/* byte-format promiscuous scans run scan_v7.cuh unless an older generation is asked for */
-	const bool use_v7 = k3 || (!known && !(env && (!strncmp(env, "v4", 2) || !strcmp(env, "v3"))));
-	const char *env7 = env && !strncmp(env, "v7", 2) ? env : NULL;
 	int64_t al = packed ? 0 : (int64_t)((32 - (reinterpret_cast<uintptr_t>(d_stream) & 31)) & 31);   /* first 32-byte boundary */
 	const int64_t head = al;                                                               /* first window of the bulk kernel */
 	/* a strip reads 64 symbols past its end and the stream holds n + 63 */
-	int64_t nstrips = n - 1 > al ? (n - 1 - al) / v3::STRIP : 0;
+	int64_t nstrips = n - 1 > al ? (n - 1 - al) / sc::STRIP : 0;
 	/* the bulk kernels carry 32-bit positions relative to a warp's run: keep a launch below
 	 * 2^31 symbols per warp (148 x 32 warps -> ~10^13 symbols); beyond that the tail kernel
 	 * below simply takes the rest */
-	if (nstrips > ((int64_t)1 << 31) / v3::STRIP * 4096) nstrips = ((int64_t)1 << 31) / v3::STRIP * 4096;
+	if (nstrips > ((int64_t)1 << 31) / sc::STRIP * 4096) nstrips = ((int64_t)1 << 31) / sc::STRIP * 4096;
 	if (nstrips < 1)      /* (never with packed input: checked above) */
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
-	const int64_t body_end = head + nstrips * v3::STRIP;
+	const int64_t body_end = head + nstrips * sc::STRIP;
 	/* packed input: the tile kernel takes the ragged tail from an expanded copy */
 	const uint8_t *d_tail = d_stream + body_end;
 	if (packed && body_end < n) {
@@ -535,17 +527,17 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		if (rc0) return rc0;
 		d_tail = ctx->d_unpack;
 	}
-	v3::xparams xp;
+	sc::xparams xp;
 	memset(&xp, 0, sizeof(xp));
 	xp.cc[0] = ctx->cc[0]; xp.cc[1] = ctx->cc[1];
 	xp.m32 = ctx->m32; xp.m33 = ctx->m33; xp.m0 = ctx->m0;
 	xp.kmax = k; xp.err_log2 = ctx->err_log2; xp.err = ctx->d_err; xp.map2g = ctx->d_map7g;
 	xp.hits = d_out; xp.max_hits = max_hits; xp.count = d_count; xp.bias = bias;
-	const int bulk_warps = 32;
+	const int bulk_warps = sc::WARPS;
 	int64_t grid = ctx->sm_count;
 	const int64_t need = (nstrips + bulk_warps - 1) / bulk_warps;
 	if (grid > need) grid = need;
-	const bool slab_mode = slab && !(env && !strcmp(env, "v3")) && !(env && !strcmp(env, "noslab"));
+	const bool slab_mode = slab != NULL;
 	if (slab_mode) {
 		const int nw = (int)grid * bulk_warps;
 		int rc2 = bt_ensure_slab(ctx, nw + 2);
@@ -556,7 +548,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	}
 	if (!ctx->d_xp)
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_xp, 16 * 128));
-	static_assert(sizeof(v3::xparams) <= 128, "xparams slot");
+	static_assert(sizeof(sc::xparams) <= 128, "xparams slot");
 	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
 	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
 	if (known) {
@@ -565,7 +557,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
 		a.ac = bt_gen_syncword(lap); a.lap = lap; a.kmax = k;
 		a.kk = k < 0 ? -1 : (k > 16 ? 16 : k);
-		a.xp = (const v3::xparams *)slot;
+		a.xp = (const sc::xparams *)slot;
 		/* each 32-bit half of the sync word has at least 16 zeros or 16 ones */
 		const uint32_t lo = (uint32_t)a.ac, hi = (uint32_t)(a.ac >> 32);
 		const bool inv = __builtin_popcount(lo) > 16, inv2 = __builtin_popcount(hi) > 16;
@@ -590,29 +582,20 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		if (ctx->prof_on) cudaEventRecord(ctx->prof_ev[0], st);
 		kern<<<(unsigned)grid, vk::WARPS * 32, vk::SMEM_BYTES, st>>>(a);
 		if (ctx->prof_on) { cudaEventRecord(ctx->prof_ev[1], st); ctx->prof_valid = 1; }
-	} else if (use_v7) {
-		/* developer switch: v7 = multiply windows, v7f = funnel-shift windows; a trailing 'a'
-		 * selects layout<1> (table A by byte permute, 32 KiB map); s4 / s6 = inline slots */
+	} else {
+		/* tables for <= 2 errors: both map levels in shared memory, table A by byte permute (layout<1>);
+		 * 3 errors: the 64 KiB first-level map (12 % of it set) and a global second level;
+		 * 4 / 5 errors: first level in global memory, positives straight to the exact test */
 		v7::args a;
-		const bool ta = !k3 && (!env7 || strchr(env7 + 2, 'a') != NULL);
+		const bool ta = !k3;
 		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
-		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const v3::xparams *)slot;
+		a.lut = ctx->d_lut7; a.map = ta ? ctx->d_map7b : ctx->d_map7; a.xp = (const sc::xparams *)slot;
 		a.m1 = 0xffffffffu; a.c64 = 64u;
 		a.map1g = reinterpret_cast<const uint8_t *>(ctx->d_map7g); a.m1g_shift = 32 - (ctx->map7g_log2 - 3);
-		void (*kern)(const v7::args) = v7::scan_promisc_v7<0, 5, 1>;       /* shipped */
-		if (env7 && !strcmp(env7, "v7")) kern = v7::scan_promisc_v7<1, 5, 0>;
-		else if (env7 && !strcmp(env7, "v7f")) kern = v7::scan_promisc_v7<0, 5, 0>;
-		else if (env7 && !strcmp(env7, "v7a")) kern = v7::scan_promisc_v7<1, 5, 1>;
-		else if (env7 && !strcmp(env7, "v7fs4")) kern = v7::scan_promisc_v7<0, 4, 0>;
-		else if (env7 && !strcmp(env7, "v7fs6")) kern = v7::scan_promisc_v7<0, 6, 0>;
-		else if (env7 && !strcmp(env7, "v7fas4")) kern = v7::scan_promisc_v7<0, 4, 1>;
-		else if (env7 && !strcmp(env7, "v7fas6")) kern = v7::scan_promisc_v7<0, 6, 1>;
-		/* 3-error tables: the 64 KiB first-level map (12 % of it set) and the global second level */
-		if (k3) kern = env7 && !strcmp(env7, "v7fs6") ? v7::scan_promisc_v7<0, 6, 0, 1> : v7::scan_promisc_v7<0, 5, 0, 1>;
-		/* 4 / 5-error tables: first level in global memory, positives straight to the exact test */
-		if (k45) kern = v7::scan_promisc_v7<0, 5, 0, 2>;
+		void (*kern)(const v7::args);
 		if (packed) kern = k45 ? v7::scan_promisc_v7<0, 5, 0, 2, true> : k3 ? v7::scan_promisc_v7<0, 5, 0, 1, true>
 				       : v7::scan_promisc_v7<0, 5, 1, 0, true>;
+		else kern = k45 ? v7::scan_promisc_v7<0, 5, 0, 2> : k3 ? v7::scan_promisc_v7<0, 5, 0, 1> : v7::scan_promisc_v7<0, 5, 1>;
 		const size_t smem = ta ? v7::layout<1>::smem_bytes : v7::layout<0>::smem_bytes;
 		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		if (k45) {
@@ -648,31 +631,6 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 			av.accessPolicyWindow.num_bytes = 0;
 			cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
 		}
-	} else if (env && !strcmp(env, "v3")) {
-		v3::args a;
-		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
-		a.lut = ctx->d_lut2; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
-		BT_CUDA_TRY(cudaFuncSetAttribute(v3::scan_promisc_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3::SMEM_BYTES));
-		v3::scan_promisc_v3<<<(unsigned)grid, v3::WARPS * 32, v3::SMEM_BYTES, st>>>(a);
-	} else {
-		v4::args a;
-		a.base = d_stream + al; a.pos0 = al; a.nstrips = nstrips;
-		a.lut = ctx->d_lut4; a.lut2 = ctx->d_lut2b; a.lut3 = ctx->d_lut3; a.map = ctx->d_map2; a.xp = (const v3::xparams *)slot;
-		/* experiment switch (developer): v4a..v4f pick LUT mode / inline slots / branch-free slots */
-		void (*kern)(const v4::args) = packed ? v4::scan_promisc_v4<2, 5, true, true> : v4::scan_promisc_v4<2, 5, true>;
-		size_t smem = v4::layout<2>::smem_bytes;
-		if (env && !strncmp(env, "v4", 2) && env[2] >= 'a' && env[2] <= 'f') smem = v4::SMEM_BYTES;
-		if (env && !strcmp(env, "v4a")) kern = v4::scan_promisc_v4<0, 5, false>;
-		else if (env && !strcmp(env, "v4b")) kern = v4::scan_promisc_v4<1, 5, true>;
-		else if (env && !strcmp(env, "v4c")) kern = v4::scan_promisc_v4<1, 4, true>;
-		else if (env && !strcmp(env, "v4d")) kern = v4::scan_promisc_v4<0, 5, true>;
-		else if (env && !strcmp(env, "v4e")) kern = v4::scan_promisc_v4<1, 6, true>;
-		else if (env && !strcmp(env, "v4f")) kern = v4::scan_promisc_v4<1, 5, false>;
-		if (env && !strcmp(env, "v4g")) { kern = v4::scan_promisc_v4<2, 5, true>; smem = v4::layout<2>::smem_bytes; }
-		else if (env && !strcmp(env, "v4h")) { kern = v4::scan_promisc_v4<2, 6, true>; smem = v4::layout<2>::smem_bytes; }
-		else if (env && !strcmp(env, "v4i")) { kern = v4::scan_promisc_v4<2, 4, true>; smem = v4::layout<2>::smem_bytes; }
-		BT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kern<<<(unsigned)grid, v4::WARPS * 32, smem, st>>>(a);
 	}
 	BT_CUDA_TRY(cudaGetLastError());
 	int rc = BTBB_B200_OK;
@@ -1036,6 +994,21 @@ extern "C" int btbb_b200_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
 {
 	if (!ctx || !n_hits) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_end: bad arguments");
 	return bt_find_ac_dev_end(ctx, n_hits);
+}
+
+extern "C" int btbb_b200_set_option(btbb_b200_ctx *ctx, int option, int64_t value)
+{
+	if (!ctx) return btbb_b200_set_error(BTBB_B200_EINVAL, "set_option: bad arguments");
+	switch (option) {
+	case BTBB_B200_OPT_TILE_KERNEL_ONLY: ctx->opt_tile_only = value != 0; break;
+	case BTBB_B200_OPT_HOST_BYTE_ROUTE: ctx->opt_host_bytes = value != 0; break;
+	case BTBB_B200_OPT_HOST_SPLIT_PERMILLE: ctx->opt_host_split = (int)(value < 0 ? 0 : value > 950 ? 950 : value); break;
+	case BTBB_B200_OPT_PACK_THREADS: ctx->opt_pack_threads = (int)(value < 0 ? 0 : value > 128 ? 128 : value); break;
+	case BTBB_B200_OPT_TRACE: ctx->opt_trace = value != 0; break;
+	case BTBB_B200_OPT_DECODE_WIDE_STAGING: ctx->opt_decode_wide = value != 0; break;
+	default: return btbb_b200_set_error(BTBB_B200_EINVAL, "set_option: unknown option");
+	}
+	return BTBB_B200_OK;
 }
 
 /* measurement hook: CUDA events around the bulk scan kernel of every following scan, on its stream */

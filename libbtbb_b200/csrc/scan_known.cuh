@@ -18,14 +18,14 @@
 
 namespace vk {
 
-using v3::ld256;
-using v3::ldg32;
-using v3::lds32;
-using v3::lds32o;
-using v3::sts32;
-using v3::pack32;
-using v3::bfind;
-using v3::xparams;
+using sc::ld256;
+using sc::ldg32;
+using sc::lds32;
+using sc::lds32o;
+using sc::sts32;
+using sc::pack32;
+using sc::bfind;
+using sc::xparams;
 
 constexpr int WARPS = 32;
 constexpr int K = 4;

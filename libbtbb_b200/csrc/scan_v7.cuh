@@ -40,17 +40,17 @@
 
 namespace v7 {
 
-using v3::ld256;
-using v3::lds32;
-using v3::lds32o;
-using v3::lds16o;
-using v3::sts32;
-using v3::sts16o;
-using v3::pack32;
-using v3::bfind;
-using v3::xparams;
-using v4::onebit;
-using v4::exact_tail;
+using sc::ld256;
+using sc::lds32;
+using sc::lds32o;
+using sc::lds16o;
+using sc::sts32;
+using sc::sts16o;
+using sc::pack32;
+using sc::bfind;
+using sc::xparams;
+using sc::onebit;
+using sc::exact_tail;
 
 constexpr int WARPS = 32;
 constexpr int K = 4;
@@ -330,9 +330,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 		if (PACKED) {
 			const uint32_t *pw = reinterpret_cast<const uint32_t *>(a.base) + s * SW + lane;
 			#pragma unroll
-			for (int k = 0; k < K; k++) wv[k] = v3::ldg32(pw + 32 * k);
+			for (int k = 0; k < K; k++) wv[k] = sc::ldg32(pw + 32 * k);
 			uint32_t halo = 0;
-			if (lane < 2) halo = v3::ldg32(pw + SW);                /* words 0 / 1 of the next strip */
+			if (lane < 2) halo = sc::ldg32(pw + SW);                /* words 0 / 1 of the next strip */
 			if (s + 1 < s_end && lane < K)
 				asm volatile("prefetch.global.L2 [%0];" :: "l"(pw - lane + SW + 32 * lane));
 			#pragma unroll

@@ -68,12 +68,8 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 	BT_CUDA_TRY(cudaMalloc(&ctx->d_bloom, bloom.size() * sizeof(uint32_t)));
 	BT_CUDA_TRY(cudaMemcpy(ctx->d_bloom, bloom.data(), bloom.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 
-	/* --- bulk-kernel tables (scan_v3.cuh): two LUTs over codeword bits 32..44 / 45..56 giving
-	 * the low 32 syndrome bits of the received part, and a single-probe bit map (word = top 14
-	 * bits, bit = low 5) of every value that part can take for an acceptable window: the
-	 * table syndromes (and zero) XOR the constant of either legal tail.  Only built while the
-	 * map stays sparse (k <= 2: at most 3424 of 2^19 bits set). --- */
-	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL; ctx->d_lut2b = NULL; ctx->d_lut3 = NULL;
+	/* --- constants of the bulk kernels' exact test: the 34-bit syndrome of PN ^ (legal tail << 57) per
+	 * Barker class, and parity masks over codeword bits 32..56 for syndrome bits 0 / 32 / 33 --- */
 	ctx->cc[0] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_A << 57));
 	ctx->cc[1] = bt_syndrome_slow(BT_PN ^ ((uint64_t)BT_BARKER_B << 57));
 	ctx->m32 = ctx->m33 = ctx->m0 = 0;
@@ -82,79 +78,6 @@ int bt_tables_build(btbb_b200_ctx *ctx, int k)
 		if (g_bit_syn[32 + j] & 1) ctx->m0 |= 1u << j;
 		if ((g_bit_syn[32 + j] >> 32) & 1) ctx->m32 |= 1u << j;
 		if ((g_bit_syn[32 + j] >> 33) & 1) ctx->m33 |= 1u << j;
-	}
-	if (k <= 2) {
-		const int abits = 13, bbits = 12;
-		std::vector<uint32_t> lut(((size_t)1 << abits) + ((size_t)1 << bbits), 0u);
-		for (uint32_t v = 0; v < (1u << abits); v++) {
-			uint64_t sy = 0;
-			for (int j = 0; j < abits; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + j];
-			lut[v] = (uint32_t)sy;
-		}
-		for (uint32_t v = 0; v < (1u << bbits); v++) {
-			uint64_t sy = 0;
-			for (int j = 0; j < bbits; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + abits + j];
-			lut[((size_t)1 << abits) + v] = (uint32_t)sy;
-		}
-		/* v4, LUTMODE 1: bits 34..46 (13) and 47..56 (10); bits 32/33 do not reach the low 32
-		 * syndrome bits */
-		{
-			std::vector<uint32_t> l2b(8192 + 1024, 0u);
-			for (uint32_t v = 0; v < 8192; v++) {
-				uint64_t sy = 0;
-				for (int j = 0; j < 13; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + j];
-				l2b[v] = (uint32_t)sy;
-			}
-			for (uint32_t v = 0; v < 1024; v++) {
-				uint64_t sy = 0;
-				for (int j = 0; j < 10; j++) if ((v >> j) & 1) sy ^= g_bit_syn[47 + j];
-				l2b[8192 + v] = (uint32_t)sy;
-			}
-			BT_CUDA_TRY(cudaMalloc(&ctx->d_lut2b, l2b.size() * sizeof(uint32_t)));
-			BT_CUDA_TRY(cudaMemcpy(ctx->d_lut2b, l2b.data(), l2b.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		}
-		/* v4, LUTMODE 2: bits 34..41 / 42..49 / 50..56 as three lane-replicated field tables */
-		{
-			std::vector<uint32_t> l3;
-			const int fw3[3] = {8, 8, 7};
-			for (int f = 0, pos = 0; f < 3; pos += fw3[f], f++)
-				for (uint32_t v = 0; v < (1u << fw3[f]); v++) {
-					uint64_t sy = 0;
-					for (int j = 0; j < fw3[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[34 + pos + j];
-					l3.push_back((uint32_t)sy);
-				}
-			BT_CUDA_TRY(cudaMalloc(&ctx->d_lut3, l3.size() * sizeof(uint32_t)));
-			BT_CUDA_TRY(cudaMemcpy(ctx->d_lut3, l3.data(), l3.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		}
-		/* v4, LUTMODE 0: the same 25 bits as four lane-replicated field tables (7, 6, 6, 6 bits) */
-		std::vector<uint32_t> lut4;
-		const int fw[4] = {7, 6, 6, 6};
-		for (int f = 0, pos = 0; f < 4; pos += fw[f], f++)
-			for (uint32_t v = 0; v < (1u << fw[f]); v++) {
-				uint64_t sy = 0;
-				for (int j = 0; j < fw[f]; j++) if ((v >> j) & 1) sy ^= g_bit_syn[32 + pos + j];
-				lut4.push_back((uint32_t)sy);
-			}
-		BT_CUDA_TRY(cudaMalloc(&ctx->d_lut4, lut4.size() * sizeof(uint32_t)));
-		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut4, lut4.data(), lut4.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		/* first-level map (2^19 bits: word = syndrome bits 18..31, bit = bits 0..4), followed by
-		 * the second-level map the v4 kernel consults after a positive (2^17 bits: word = bits
-		 * 10..21, bit = bits 5..9) */
-		const size_t m1_words = (size_t)1 << (19 - 5), m2_words = (size_t)1 << (17 - 5);
-		std::vector<uint32_t> map(m1_words + m2_words, 0u);
-		auto map_add = [&](uint32_t s32) {
-			for (int c = 0; c < 2; c++) {
-				uint32_t v = s32 ^ (uint32_t)ctx->cc[c];
-				map[v >> 18] |= 1u << (v & 31);
-				map[m1_words + ((v >> 10) & (m2_words - 1))] |= 1u << ((v >> 5) & 31);
-			}
-		};
-		map_add(0);
-		for (auto &e : ents) map_add((uint32_t)e.syn);
-		BT_CUDA_TRY(cudaMalloc(&ctx->d_lut2, lut.size() * sizeof(uint32_t)));
-		BT_CUDA_TRY(cudaMemcpy(ctx->d_lut2, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-		BT_CUDA_TRY(cudaMalloc(&ctx->d_map2, map.size() * sizeof(uint32_t)));
-		BT_CUDA_TRY(cudaMemcpy(ctx->d_map2, map.data(), map.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 	}
 
 	/* v7 (scan_v7.cuh) works on syndrome bits 1..32: field tables A / B / C over
@@ -268,11 +191,6 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	if (ctx->d_bloom) cudaFree(ctx->d_bloom);
 	if (ctx->d_err) cudaFree(ctx->d_err);
 	free(ctx->h_err); ctx->h_err = NULL;
-	if (ctx->d_lut2) cudaFree(ctx->d_lut2);
-	if (ctx->d_map2) cudaFree(ctx->d_map2);
-	if (ctx->d_lut4) cudaFree(ctx->d_lut4);
-	if (ctx->d_lut2b) cudaFree(ctx->d_lut2b);
-	if (ctx->d_lut3) cudaFree(ctx->d_lut3);
 	if (ctx->d_lut7) cudaFree(ctx->d_lut7);
 	if (ctx->d_map7) cudaFree(ctx->d_map7);
 	if (ctx->d_map7b) cudaFree(ctx->d_map7b);
@@ -280,5 +198,4 @@ void bt_tables_free(btbb_b200_ctx *ctx)
 	ctx->d_map7g = NULL;
 	ctx->d_lut7 = NULL; ctx->d_map7 = NULL; ctx->d_map7b = NULL;
 	ctx->d_tables = NULL; ctx->d_bloom = NULL; ctx->d_err = NULL;
-	ctx->d_lut2 = NULL; ctx->d_map2 = NULL; ctx->d_lut4 = NULL; ctx->d_lut2b = NULL; ctx->d_lut3 = NULL;
 }

@@ -121,6 +121,53 @@ double ref_find_all_mt(char *stream, int64_t search_length, uint32_t lap,
 	return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* the same partition, keeping the hits: thread t's list is that of [begin_t, end_t) with global offsets,
+ * and the concatenation in thread order is the ascending list of the whole range (ranges partition the
+ * positions; each window is tested on its own).  Returns the total; at most max_hits are stored. */
+typedef struct { char *stream; int64_t begin, end; uint32_t lap; int k; ref_hit *buf; int64_t cap, n; } ref_job2;
+
+static void *ref_worker2(void *arg)
+{
+	ref_job2 *j = (ref_job2 *)arg;
+	int64_t i;
+	for (;;) {
+		j->n = ref_find_all(j->stream + j->begin, j->end - j->begin, j->lap, j->k, j->buf, j->cap);
+		if (j->n <= j->cap) break;
+		free(j->buf); j->cap = j->n + 16;
+		j->buf = (ref_hit *)malloc((size_t)j->cap * sizeof(ref_hit));
+	}
+	for (i = 0; i < j->n; i++) j->buf[i].offset += j->begin;
+	return NULL;
+}
+
+int64_t ref_find_all_mt_hits(char *stream, int64_t search_length, uint32_t lap, int max_ac_errors, int threads,
+			     ref_hit *hits, int64_t max_hits)
+{
+	pthread_t tid[256];
+	ref_job2 job[256];
+	int64_t total = 0;
+	int t;
+	if (threads < 1) threads = 1;
+	if (threads > 256) threads = 256;
+	for (t = 0; t < threads; t++) {
+		job[t].stream = stream;
+		job[t].begin = search_length * t / threads;
+		job[t].end = search_length * (t + 1) / threads;
+		job[t].lap = lap; job[t].k = max_ac_errors; job[t].n = 0;
+		job[t].cap = (job[t].end - job[t].begin) / 2000 + 1024;
+		job[t].buf = (ref_hit *)malloc((size_t)job[t].cap * sizeof(ref_hit));
+		pthread_create(&tid[t], NULL, ref_worker2, &job[t]);
+	}
+	for (t = 0; t < threads; t++) {
+		int64_t i;
+		pthread_join(tid[t], NULL);
+		for (i = 0; i < job[t].n; i++, total++)
+			if (total < max_hits) hits[total] = job[t].buf[i];
+		free(job[t].buf);
+	}
+	return total;
+}
+
 /* ---- per-packet chain, silent (btbb_decode prints; call the two halves) ---- */
 typedef struct {
 	int32_t header_ok;       /* btbb_decode_header return */

@@ -292,9 +292,9 @@ def test_packed_and_byte_ingest_with_larger_tables(product_lib, k_init):
         assert rc == 0 and d_hits[:cnt].cpu().numpy().tobytes() == want.tobytes(), ("bytes", cnt, len(want))
 
 
-def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc, monkeypatch):
+def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc):
     """>= 4 Mi symbols: find_ac_host packs on the host before the copy; the byte-format copy
-    (BTBB_B200_HOST=bytes) and the oracle must give the same records, pageable memory included."""
+    (BTBB_B200_OPT_HOST_BYTE_ROUTE) and the oracle must give the same records, pageable memory included."""
     assert orc.orc_init(2) == 0
     rng = np.random.default_rng(99)
     n = 6_000_011
@@ -305,15 +305,15 @@ def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc, monkeypatch):
         want = util.find_all(orc, "orc", s, n, lap, k)
         got = gpu_ctx2.find_ac_host(s, n, lap, k)
         assert got.tobytes() == want.tobytes(), (hex(lap), k, len(got), len(want))
-        monkeypatch.setenv("BTBB_B200_HOST", "bytes")
+        gpu_ctx2.set_option(B.OPT_HOST_BYTE_ROUTE, 1)
         got2 = gpu_ctx2.find_ac_host(s, n, lap, k)
-        monkeypatch.delenv("BTBB_B200_HOST")
+        gpu_ctx2.set_option(B.OPT_HOST_BYTE_ROUTE, 0)
         assert got2.tobytes() == want.tobytes(), ("bytes", hex(lap), k)
         # head as bytes over DMA, rest packed (what a pinned buffer gets), forced split points
-        for frac in ("0.37", "0.0007", "0.95"):
-            monkeypatch.setenv("BTBB_B200_HOST_SPLIT", frac)
+        for frac in (370, 1, 950):
+            gpu_ctx2.set_option(B.OPT_HOST_SPLIT_PERMILLE, frac)
             got3 = gpu_ctx2.find_ac_host(s, n, lap, k)
-            monkeypatch.delenv("BTBB_B200_HOST_SPLIT")
+            gpu_ctx2.set_option(B.OPT_HOST_SPLIT_PERMILLE, 0)
             assert got3.tobytes() == want.tobytes(), ("split", frac, hex(lap), k)
     import torch
     pinned = torch.from_numpy(s).pin_memory()
@@ -325,12 +325,10 @@ def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc, monkeypatch):
     import ctypes as C
     few = np.zeros(50, dtype=B.HIT_DTYPE)
     cnt = C.c_int64(0)
-    for env in (None, "0.5"):
-        if env:
-            monkeypatch.setenv("BTBB_B200_HOST_SPLIT", env)
+    for env in (0, 500):
+        gpu_ctx2.set_option(B.OPT_HOST_SPLIT_PERMILLE, env)
         rc = B.lib().btbb_b200_find_ac_host(gpu_ctx2.h, s.ctypes.data, n, B.LAP_ANY, 2, few.ctypes.data, 50, C.byref(cnt))
-        if env:
-            monkeypatch.delenv("BTBB_B200_HOST_SPLIT")
+        gpu_ctx2.set_option(B.OPT_HOST_SPLIT_PERMILLE, 0)
         assert rc == -4 and cnt.value == len(want), (env, rc, cnt.value)
         wanted = {r.tobytes() for r in want}
         assert all(r.tobytes() in wanted for r in few) and (np.diff(few["offset"]) > 0).all(), env

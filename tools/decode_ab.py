@@ -1,5 +1,5 @@
 """A/B of decode-kernel launch configurations (developer tool): TRY_CLOCKS kernel time on the
-config-3 capture for each BTBB_B200_DECODE_CFG value given on the command line."""
+config-3 capture for the default (24 warps x 16 staged records) and `wide` (12 x 32)."""
 import ctypes as C, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -24,10 +24,7 @@ pk[:, 17] = 1
 out = torch.empty((cnt * 64, 372), dtype=torch.uint8, device="cuda")
 res, ref = {}, None
 for name in sys.argv[1:] or ["default"]:
-    if name == "default":
-        os.environ.pop("BTBB_B200_DECODE_CFG", None)
-    else:
-        os.environ["BTBB_B200_DECODE_CFG"] = name
+    ctx.set_option(B.OPT_DECODE_WIDE_STAGING, 1 if name == "wide" else 0)      # names: default, wide
     out.zero_()
     for _ in range(3):
         B.check(lib.btbb_b200_decode_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, 1, out.data_ptr(), st))

@@ -16,8 +16,7 @@ hits = np.zeros(cap, dtype=B.HIT_DTYPE); got = C.c_int64(0)
 import os as _os
 print("host threads", _os.cpu_count())
 for nt in _os.environ.get("PROBE_THREADS", "0").split(","):
-  if nt != "0":
-    _os.environ["BTBB_B200_PACK_THREADS"] = nt
+  ctx.set_option(B.OPT_PACK_THREADS, int(nt))
   for name, ptr in (("pinned", hp.data_ptr()), ("pageable", hn.ctypes.data)):
     for it in range(4):
         t = time.perf_counter()
