@@ -438,6 +438,10 @@ int ref_hop_winnow(uint32_t address, const uint8_t *afh_map, int aliased, uint32
 		pn->used_channels = 79;
 	pn->clk_offset = (int)(known6 & 0x3f);
 	pn->first_pkt_time = 0;
+	/* init_candidates / channel_winnow read pn->aliased (:463, :583), which nothing in the library ever
+	 * sets (btbb_init_hop_reversal only records the BTBB_IS_ALIASED flag, :494): a receiver that aliases
+	 * has to set the field itself, as done here */
+	pn->aliased = aliased;
 	for (j = 0; j < n_obs && j < MAX_PATTERN_LENGTH; j++) {
 		pn->pattern_indices[j] = indices[j];
 		pn->pattern_channels[j] = channels[j];
