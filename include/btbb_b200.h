@@ -113,8 +113,10 @@ int btbb_b200_find_ac_dev(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t s
  * btbb_b200_find_ac_dev in two halves, for callers that pipeline: _begin enqueues the scan and
  * the ordering pass on cuda_stream and returns without waiting; _end waits for them and
  * delivers the count and the status (in the uncommon cases -- known-LAP scans, very dense
- * hits -- it still has work to enqueue and wait for).  One call can be pending per context;
- * d_hits must stay untouched in between.  btbb_b200_find_ac_dev is _begin followed by _end.
+ * hits -- it still has work to enqueue and wait for).  TWO calls can be pending per context, each
+ * with its own d_hits (untouched in between); _end completes the OLDEST one.  A caller that begins
+ * scan i + 1 before it ends scan i keeps the GPU busy across its own host work and the library's
+ * launch latency.  btbb_b200_find_ac_dev is _begin followed by _end.
  */
 int btbb_b200_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t search_length,
 				uint32_t lap, int max_ac_errors,
@@ -278,10 +280,11 @@ int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t str
  * stream from a device buffer holding that range plus 63 more symbols (the north star fixes the
  * seam overlap at 72); the kernels report GLOBAL offsets.  Ranges partition the positions, so the
  * rank-order concatenation of the per-rank sorted lists is the sorted list of the whole stream.
- * The records travel over NVLink peer memory (CUDA IPC mapped gather buffers, plain device-to-device
- * copies on a copy stream, so the exchange of one scan runs underneath the next scan) or, with
- * BTBB_B200_SHARD_NCCL_ONLY or where peer mapping fails, as an NCCL allgatherv (one all-gather of
- * the counts + one group of exact-size broadcasts).  NCCL (libnccl.so.2) is loaded on first use.
+ * The records travel over NVLink peer memory: every rank's gather buffer is mapped into every other
+ * rank (CUDA IPC) and the kernel that orders a scan's hits stores each record into its slot on all
+ * GPUs as it writes the local list -- the all-gather is fused into the ordering pass.  With
+ * BTBB_B200_SHARD_NCCL_ONLY, or where peer mapping fails, the exchange is an NCCL allgatherv (one
+ * all-gather of the counts + one group of exact-size broadcasts).  NCCL (libnccl.so.2) is loaded on first use.
  *
  *   rank 0:      btbb_b200_shard_unique_id(id); hand the 128 bytes to every rank (any transport)
  *   every rank:  btbb_b200_shard_init(ctx, id, rank, world, slot_records, flags)
@@ -294,7 +297,8 @@ int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t str
  * slot_records bounds the hits ONE rank may report per scan (BTBB_B200_EOVERFLOW beyond).
  */
 #define BTBB_B200_SHARD_ID_BYTES 128
-#define BTBB_B200_SHARD_NCCL_ONLY 1
+#define BTBB_B200_SHARD_NCCL_ONLY 1       /* exchange = NCCL allgatherv after each scan */
+#define BTBB_B200_SHARD_COPY_ENGINES 2    /* peer memory, but pushed by the copy engines after the scan instead of stored by the ordering kernel */
 int btbb_b200_shard_unique_id(void *id);
 int btbb_b200_shard_init(btbb_b200_ctx *ctx, const void *id, int rank, int world, int64_t slot_records, int flags);
 int btbb_b200_shard_info(const btbb_b200_ctx *ctx, int *rank, int *world, int *peer_memory);

@@ -70,6 +70,19 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	btbb_b200_shard_destroy(ctx);
+	{
+		const bt_lane &o = ctx->parked;      /* the inactive lane's scratch */
+		if (o.d_count) cudaFree(o.d_count);
+		if (o.d_tmp) cudaFree(o.d_tmp);
+		if (o.d_sort_hist) cudaFree(o.d_sort_hist);
+		if (o.d_slab) cudaFree(o.d_slab);
+		if (o.d_slab_cnt) cudaFree(o.d_slab_cnt);
+		if (o.d_slab_base) cudaFree(o.d_slab_base);
+		if (o.h_res) cudaFreeHost(o.h_res);
+		if (o.ev_done) cudaEventDestroy(o.ev_done);
+		for (int i = 0; i < 2; i++) if (o.prof_ev[i]) cudaEventDestroy(o.prof_ev[i]);
+		if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+	}
 	bt_tables_free(ctx);
 	if (ctx->d_count) cudaFree(ctx->d_count);
 	if (ctx->d_tmp) cudaFree(ctx->d_tmp);
@@ -198,6 +211,8 @@ static int scan_host(btbb_b200_ctx *ctx, const char *stream, int64_t search_leng
 		     unsigned long long *first_key)
 {
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	if (ctx->lane_count) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_host: device scans are pending on this context");
+	bt_lane_reset(ctx);
 	int64_t chunk = 0;
 	int rc = scan_host_prepare(ctx, search_length, max_hits, first_key != NULL, &chunk);
 	if (rc) return rc;
@@ -373,6 +388,8 @@ static int scan_host_packed(btbb_b200_ctx *ctx, const char *stream, int64_t sear
 			    int max_ac_errors, btbb_b200_hit *hits, int64_t max_hits, int64_t *n_hits)
 {
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	if (ctx->lane_count) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_host: device scans are pending on this context");
+	bt_lane_reset(ctx);
 	const bool trace = ctx->opt_trace != 0;
 	const double t0 = trace ? now_ms() : 0;
 	int64_t split = 0;

@@ -31,6 +31,28 @@ struct bt_pending {
 	uint32_t lap;
 	btbb_b200_hit *d_hits;
 	cudaStream_t st;
+	int fanned;          /* the ordering pass also stored the records into ctx->d_fan's lists */
+};
+
+/* Per-scan scratch of the device entry points.  Two scans may be pending on one context (the second is
+ * enqueued before the first is waited for, so the GPU never idles between them): the context's own
+ * fields of the same names are the ACTIVE lane's, the other lane's values are parked here
+ * (bt_lane_select, find_ac.cu). */
+struct bt_lane {
+	unsigned long long *d_count;
+	btbb_b200_hit *d_tmp;
+	int64_t tmp_cap;
+	uint32_t *d_sort_hist;
+	int64_t sort_hist_cap;
+	btbb_b200_hit *d_slab;
+	uint32_t *d_slab_cnt;
+	unsigned long long *d_slab_base;
+	int slab_n;
+	unsigned long long *h_res;
+	bt_pending pending;
+	cudaEvent_t ev_done;         /* everything begin() enqueued for this scan has finished */
+	cudaEvent_t prof_ev[2];
+	int prof_valid;
 };
 
 struct bt_shard;
@@ -95,6 +117,12 @@ struct btbb_b200_ctx {
 	int opt_tile_only, opt_host_bytes, opt_host_split, opt_pack_threads, opt_trace, opt_decode_wide;   /* btbb_b200_set_option */
 	cudaEvent_t prof_ev[2];      /* btbb_b200_set_profiling: around the bulk scan kernel */
 	int prof_on, prof_valid;
+	cudaEvent_t ev_done;         /* active lane: the pending scan's last enqueued operation */
+	bt_lane parked;              /* the inactive lane */
+	int lane_active, lane_head, lane_count;   /* which lane the fields above belong to; oldest pending lane; pending scans (0..2) */
+	btbb_b200_hit *const *d_fan; /* multi-GPU fan-out of the next scan's ordered records (device array of list pointers), see sharded.cu */
+	int fan_n;
+	int last_fanned;             /* the scan just ended delivered its records through the fan-out */
 	bt_shard *shard;             /* multi-GPU state (sharded.cu), NULL until btbb_b200_shard_init */
 	std::mutex *host_lock;       /* serialises the host-buffer entry points, which share the scratch above */
 };
@@ -121,6 +149,7 @@ int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits);
 int bt_find_ac_dev_impl(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
 			int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, int64_t *n_hits, cudaStream_t st);
 int bt_ensure_tmp(btbb_b200_ctx *ctx, int64_t hits);
+void bt_lane_reset(btbb_b200_ctx *ctx);
 int bt_scan_launch(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, uint32_t lap, int k,
 		   btbb_b200_hit *d_out, int64_t max_hits, unsigned long long *d_count,
 		   int64_t bias, cudaStream_t st);

@@ -682,7 +682,8 @@ namespace {
 /* one block: slab order is head (index nw), runs 0..nw-1, tail (nw+1).  Writes the exclusive
  * bases (64-bit) into base[0..nw+2), the total into out[0] and an overflow flag into out[1]. */
 __global__ void __launch_bounds__(1024) slab_scan_kernel(uint32_t *cnt, const unsigned long long *edge, int nw,
-							 unsigned long long *base, unsigned long long *out)
+							 unsigned long long *base, unsigned long long *out,
+							 btbb_b200_hit *const *fan, int fan_n)
 {
 	__shared__ unsigned long long wsum[32];
 	__shared__ unsigned long long carry_s;
@@ -732,11 +733,21 @@ __global__ void __launch_bounds__(1024) slab_scan_kernel(uint32_t *cnt, const un
 		__syncthreads();
 	}
 	if (t == 0) { out[0] = carry_s; out[1] = (unsigned long long)over; }
+	/* fan-out (multi-GPU): the record in front of every destination list is its header, the hit count */
+	if (t < fan_n) {
+		btbb_b200_hit hdr;
+		hdr.offset = (int64_t)carry_s; hdr.lap = 0; hdr.ac_errors = 0; hdr.pad[0] = hdr.pad[1] = hdr.pad[2] = 0;
+		fan[t][-1] = hdr;
+	}
 }
 
 /* one block per slab: bitonic sort of <= BT_SLAB_CAP records by offset, written to its place */
+/* fan / fan_n (multi-GPU, sharded.cu): every record is also stored into fan_n further lists -- this rank's
+ * slot of the gather buffer on every GPU of the node, peer memory written straight from the kernel over
+ * NVLink: the all-gather of the hit records is part of the ordering pass */
 __global__ void __launch_bounds__(256) slab_sort_kernel(const btbb_b200_hit *slab, const uint32_t *cnt,
-							const unsigned long long *base, btbb_b200_hit *out, int64_t max_hits)
+							const unsigned long long *base, btbb_b200_hit *out, int64_t max_hits,
+							btbb_b200_hit *const *fan, int fan_n)
 {
 	__shared__ long long key[BT_SLAB_CAP];
 	__shared__ unsigned long long val[BT_SLAB_CAP];
@@ -776,6 +787,7 @@ __global__ void __launch_bounds__(256) slab_sort_kernel(const btbb_b200_hit *sla
 			h.offset = key[i]; h.lap = (uint32_t)(val[i] >> 8); h.ac_errors = (uint8_t)(val[i] & 0xff);
 			h.pad[0] = h.pad[1] = h.pad[2] = 0;
 			out[b0 + i] = h;
+			for (int j = 0; j < fan_n; j++) fan[j][b0 + i] = h;
 		}
 	}
 }
@@ -863,16 +875,72 @@ extern "C" int btbb_b200_find_ac_packed_dev(btbb_b200_ctx *ctx, const uint32_t *
  * the kernels: begin() enqueues everything the common case needs -- scan, slab scan, slab sort,
  * the read-back of the counters into pinned memory -- and returns; end() waits, and only in the
  * uncommon cases (no slab ordering for this call, or a slab overflowed) runs the generic path. */
+/* swap the context's per-scan scratch with the parked lane's so that lane `want` is the active one */
+static void bt_lane_select(btbb_b200_ctx *ctx, int want)
+{
+	if (ctx->lane_active == want) return;
+	bt_lane cur;
+	cur.d_count = ctx->d_count; cur.d_tmp = ctx->d_tmp; cur.tmp_cap = ctx->tmp_cap;
+	cur.d_sort_hist = ctx->d_sort_hist; cur.sort_hist_cap = ctx->sort_hist_cap;
+	cur.d_slab = ctx->d_slab; cur.d_slab_cnt = ctx->d_slab_cnt; cur.d_slab_base = ctx->d_slab_base; cur.slab_n = ctx->slab_n;
+	cur.h_res = ctx->h_res; cur.pending = ctx->pending; cur.ev_done = ctx->ev_done;
+	cur.prof_ev[0] = ctx->prof_ev[0]; cur.prof_ev[1] = ctx->prof_ev[1]; cur.prof_valid = ctx->prof_valid;
+	const bt_lane &o = ctx->parked;
+	ctx->d_count = o.d_count; ctx->d_tmp = o.d_tmp; ctx->tmp_cap = o.tmp_cap;
+	ctx->d_sort_hist = o.d_sort_hist; ctx->sort_hist_cap = o.sort_hist_cap;
+	ctx->d_slab = o.d_slab; ctx->d_slab_cnt = o.d_slab_cnt; ctx->d_slab_base = o.d_slab_base; ctx->slab_n = o.slab_n;
+	ctx->h_res = o.h_res; ctx->pending = o.pending; ctx->ev_done = o.ev_done;
+	ctx->prof_ev[0] = o.prof_ev[0]; ctx->prof_ev[1] = o.prof_ev[1]; ctx->prof_valid = o.prof_valid;
+	ctx->parked = cur;
+	ctx->lane_active = want;
+}
+
+/* before anything that uses the scratch outside begin / end (host-buffer entry points, destroy): lane 0 */
+void bt_lane_reset(btbb_b200_ctx *ctx) { bt_lane_select(ctx, 0); }
+
+static int find_ac_begin_lane(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			      int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, cudaStream_t st);
+static int find_ac_end_lane(btbb_b200_ctx *ctx, int64_t *n_hits);
+
+/* Up to two scans may be pending: begin takes the free lane, end completes the OLDEST pending scan. */
 int bt_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
 			 int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, cudaStream_t st)
 {
+	if (ctx->lane_count >= 2)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: two calls are already pending on this context");
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
+	bt_lane_select(ctx, (ctx->lane_head + ctx->lane_count) & 1);
+	if (!ctx->d_count) BT_CUDA_TRY(cudaMalloc(&ctx->d_count, 2 * sizeof(unsigned long long)));
+	if (!ctx->ev_done) BT_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming));
+	if (ctx->prof_on && !ctx->prof_ev[0]) {
+		BT_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[0]));
+		BT_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[1]));
+	}
+	const int rc = find_ac_begin_lane(ctx, d_stream, packed, search_length, lap, max_ac_errors, d_hits, max_hits, st);
+	if (rc == BTBB_B200_OK) ctx->lane_count++;
+	return rc;
+}
+
+int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
+{
+	*n_hits = 0;
+	if (ctx->lane_count == 0)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: no call is pending on this context");
+	bt_lane_select(ctx, ctx->lane_head);
+	ctx->lane_head ^= 1;
+	ctx->lane_count--;
+	return find_ac_end_lane(ctx, n_hits);
+}
+
+static int find_ac_begin_lane(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed, int64_t search_length, uint32_t lap,
+			      int max_ac_errors, btbb_b200_hit *d_hits, int64_t max_hits, cudaStream_t st)
+{
 	bt_pending &pd = ctx->pending;
 	if (pd.mode != BT_PENDING_NONE)
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: a call is already pending on this context");
 	pd.d_stream = d_stream; pd.packed = packed; pd.search_length = search_length; pd.lap = lap;
 	pd.max_ac_errors = max_ac_errors; pd.d_hits = d_hits; pd.max_hits = max_hits; pd.st = st;
-	pd.bias = ctx->hit_bias;
+	pd.bias = ctx->hit_bias; pd.fanned = 0;
 	pd.mode = BT_PENDING_GENERIC;
 	if (search_length == 0) { pd.mode = BT_PENDING_EMPTY; return BTBB_B200_OK; }
 	int rc = bt_ensure_tmp(ctx, max_hits > 0 ? max_hits : 1);
@@ -891,23 +959,26 @@ int bt_find_ac_dev_begin(btbb_b200_ctx *ctx, const uint8_t *d_stream, int packed
 	if (req.used) {
 		const int nw = req.nw;
 		unsigned long long *edge_cnt = (unsigned long long *)(ctx->d_slab_cnt + ((nw + 2 + 1) & ~1));
-		slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count);
+		slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count, ctx->d_fan, ctx->fan_n);
 		/* the sort is safe to run even if a slab overflowed (counts are clamped); its output is
 		 * then simply not used */
-		slab_sort_kernel<<<nw + 2, 256, 0, st>>>(ctx->d_slab, ctx->d_slab_cnt, ctx->d_slab_base, d_hits, max_hits);
+		slab_sort_kernel<<<nw + 2, 256, 0, st>>>(ctx->d_slab, ctx->d_slab_cnt, ctx->d_slab_base, d_hits, max_hits, ctx->d_fan, ctx->fan_n);
+		pd.fanned = ctx->fan_n > 0;
 		pd.mode = BT_PENDING_SLAB;
 	} else
 		pd.mode = BT_PENDING_UNORDERED;      /* the unordered list is in d_tmp, its length in d_count[0] */
 	e = cudaMemcpyAsync(ctx->h_res, ctx->d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done, st);
 	if (e == cudaSuccess) e = cudaGetLastError();
 	if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "find_ac: enqueue"); }
 	return BTBB_B200_OK;
 }
 
-int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
+static int find_ac_end_lane(btbb_b200_ctx *ctx, int64_t *n_hits)
 {
 	bt_pending pd = ctx->pending;
 	ctx->pending.mode = BT_PENDING_NONE;
+	ctx->last_fanned = 0;
 	*n_hits = 0;
 	if (pd.mode == BT_PENDING_NONE)
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac: no call is pending on this context");
@@ -922,13 +993,15 @@ int bt_find_ac_dev_end(btbb_b200_ctx *ctx, int64_t *n_hits)
 	unsigned long long total = 0;
 	int rc;
 	if (pd.mode == BT_PENDING_SLAB || pd.mode == BT_PENDING_UNORDERED) {
-		BT_CUDA_TRY(cudaStreamSynchronize(st));
+		/* this scan's own completion, not the stream's: a second scan may already be queued behind it */
+		BT_CUDA_TRY(cudaEventSynchronize(ctx->ev_done));
 		if (ctx->h_res[0] >> 62)
 			return btbb_b200_set_error(BTBB_B200_ECUDA, "find_ac: unexpected shared-memory window layout");
 		if (pd.mode == BT_PENDING_SLAB) {
 			if (!ctx->h_res[1]) {
 				total = ctx->h_res[0];
 				*n_hits = (int64_t)total;
+				ctx->last_fanned = pd.fanned && (int64_t)total <= max_hits;
 				if ((int64_t)total > max_hits)
 					return btbb_b200_set_error(BTBB_B200_EOVERFLOW, "find_ac: hit buffer too small");
 				return BTBB_B200_OK;
@@ -1015,13 +1088,8 @@ extern "C" int btbb_b200_set_option(btbb_b200_ctx *ctx, int option, int64_t valu
 extern "C" int btbb_b200_set_profiling(btbb_b200_ctx *ctx, int on)
 {
 	if (!ctx) return btbb_b200_set_error(BTBB_B200_EINVAL, "set_profiling: bad arguments");
-	BT_CUDA_TRY(cudaSetDevice(ctx->device));
-	if (on && !ctx->prof_ev[0]) {
-		BT_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[0]));
-		BT_CUDA_TRY(cudaEventCreate(&ctx->prof_ev[1]));
-	}
 	ctx->prof_on = on != 0;
-	ctx->prof_valid = 0;
+	ctx->prof_valid = 0; ctx->parked.prof_valid = 0;      /* the events themselves are created per lane, at its next scan */
 	return BTBB_B200_OK;
 }
 

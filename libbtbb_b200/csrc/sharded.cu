@@ -11,11 +11,14 @@
  *
  * Two forms of the exchange:
  *   peer memory (default)  every rank owns a gather buffer of world slots x 2 generations,
- *       mapped into every peer with CUDA IPC.  After its scan a rank pushes [count header |
- *       records] into its slot on every peer with plain device-to-device copies on a copy
- *       stream: the scan kernel holds every SM (one persistent CTA per SM), copy engines are the
- *       only thing that runs beside it, and NVLink moves the few megabytes while the NEXT scan
- *       is already under way (begin(i + 1) may be enqueued before end(i) pushes).
+ *       mapped into every peer with CUDA IPC.  The ordering kernel of a scan (slab_sort_kernel,
+ *       find_ac.cu) stores every record it places not only into the local list but also into this
+ *       rank's slot on EVERY GPU -- plain stores to peer memory over NVLink, a few megabytes spread
+ *       over the kernel's own run time -- and the slab-scan kernel writes the count header the same
+ *       way: the all-gather is fused into the ordering pass, costs no launch, no copy-engine
+ *       descriptor and no host call, and is complete when the scan's stream is.  Scans that do not
+ *       take the slab path (known LAP, very dense hits) and BTBB_B200_SHARD_COPY_ENGINES push
+ *       [count header | records] with device-to-device copies on a copy stream instead, after the scan.
  *   NCCL allgatherv         one ncclAllGather of the counts, then one group of ncclBroadcasts with
  *       exact sizes (NCCL has no native allgatherv).  Needs SMs, so it runs after the scan.
  * NCCL is loaded with dlopen (libnccl.so.2: the copy already in the process when the caller is a
@@ -87,6 +90,7 @@ constexpr int BT_SHARD_MAX_WORLD = 64;
 
 struct bt_shard {
 	int rank, world, peer;               /* peer = 1: peer-memory exchange available */
+	int flags, last_fanned;
 	int64_t slot;                        /* records per slot (without the header record) */
 	ncclComm_t comm;
 	cudaStream_t copy;                   /* the exchange's own stream: never waits for the scan stream */
@@ -98,9 +102,11 @@ struct bt_shard {
 	cudaEvent_t sent[2];
 	int sent_valid[2];
 	int gen;                             /* generation the next begin() writes */
-	int last;                            /* generation of the most recent push, -1 = none */
-	int pending;                         /* begin() without end() */
+	int last;                            /* generation of the most recently ended scan, -1 = none */
+	int pending;                         /* scans begun and not ended yet (0..2); the oldest one's generation is pend_g[0] */
+	int pend_g[2];
 	int64_t n_last;
+	btbb_b200_hit **d_fan[2];            /* per generation: this rank's slot (first record) in every rank's gather buffer */
 	int *d_flag;                         /* barrier scratch */
 	int64_t *d_cnt;                      /* allgatherv: counts */
 };
@@ -136,6 +142,7 @@ extern "C" int btbb_b200_shard_destroy(btbb_b200_ctx *ctx)
 	}
 	if (s->h_hdr) cudaFreeHost(s->h_hdr);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
+	for (int g = 0; g < 2; g++) if (s->d_fan[g]) cudaFree(s->d_fan[g]);
 	if (s->d_flag) cudaFree(s->d_flag);
 	if (s->d_cnt) cudaFree(s->d_cnt);
 	if (s->copy) cudaStreamDestroy(s->copy);
@@ -156,7 +163,7 @@ extern "C" int btbb_b200_shard_init(btbb_b200_ctx *ctx, const void *id, int rank
 	bt_shard *s = (bt_shard *)calloc(1, sizeof(*s));
 	if (!s) return btbb_b200_set_error(BTBB_B200_ENOMEM, "shard_init: out of host memory");
 	ctx->shard = s;
-	s->rank = rank; s->world = world; s->slot = slot_records; s->last = -1;
+	s->rank = rank; s->world = world; s->slot = slot_records; s->last = -1; s->flags = flags;
 	ncclUniqueId uid;
 	memcpy(&uid, id, sizeof(uid));
 	ncclResult_t nr = g_nccl.CommInitRank(&s->comm, world, uid, rank);
@@ -211,6 +218,15 @@ extern "C" int btbb_b200_shard_init(btbb_b200_ctx *ctx, const void *id, int rank
 		s->peer = h_ok;
 	} else if (world == 1)
 		s->peer = 1;
+	if (s->peer) {
+		/* fan-out lists of the ordering kernel: slot [g][rank] on every GPU, records start behind the header */
+		for (int g = 0; g < 2; g++) {
+			btbb_b200_hit *h_fan[BT_SHARD_MAX_WORLD];
+			for (int r = 0; r < world; r++) h_fan[r] = slot_ptr(s, s->peers[r], g, rank) + 1;
+			BT_TRY_OR_DESTROY(cudaMalloc(&s->d_fan[g], (size_t)world * sizeof(btbb_b200_hit *)));
+			BT_TRY_OR_DESTROY(cudaMemcpy(s->d_fan[g], h_fan, (size_t)world * sizeof(btbb_b200_hit *), cudaMemcpyHostToDevice));
+		}
+	}
 #undef BT_TRY_OR_DESTROY
 	return BTBB_B200_OK;
 }
@@ -238,7 +254,7 @@ extern "C" int btbb_b200_find_ac_sharded_begin(btbb_b200_ctx *ctx, const uint8_t
 {
 	if (!ctx || !ctx->shard) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_sharded: btbb_b200_shard_init first");
 	bt_shard *s = ctx->shard;
-	if (s->pending) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_sharded: a scan is already pending");
+	if (s->pending >= 2) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_sharded: two scans are already pending");
 	if ((!d_stream && search_length > 0) || search_length < 0 || (lap != BTBB_B200_LAP_ANY && lap > 0xffffffu))
 		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_sharded: bad arguments");
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -247,10 +263,15 @@ extern "C" int btbb_b200_find_ac_sharded_begin(btbb_b200_ctx *ctx, const uint8_t
 	if (s->sent_valid[g]) BT_CUDA_TRY(cudaEventSynchronize(s->sent[g]));
 	const int64_t saved = ctx->hit_bias;
 	ctx->hit_bias = first_position;
+	/* peer memory: the ordering kernel stores every record into this rank's slot on every GPU as it writes
+	 * the sorted list (promiscuous bulk path; other paths fall back to the copy-engine push in _end) */
+	if (s->peer && !(s->flags & BTBB_B200_SHARD_COPY_ENGINES)) { ctx->d_fan = s->d_fan[g]; ctx->fan_n = s->world; }
 	int rc = bt_find_ac_dev_begin(ctx, d_stream, 0, search_length, lap, max_ac_errors, s->local[g] + 1, s->slot, (cudaStream_t)cuda_stream);
+	ctx->d_fan = NULL; ctx->fan_n = 0;
 	ctx->hit_bias = saved;
 	if (rc) return rc;
-	s->pending = 1;
+	s->pend_g[s->pending++] = g;
+	s->gen ^= 1;
 	return BTBB_B200_OK;
 }
 
@@ -259,14 +280,16 @@ static int shard_end_wait(btbb_b200_ctx *ctx, int64_t *n_local, int *g_out)
 {
 	bt_shard *s = ctx->shard;
 	if (!s->pending) return btbb_b200_set_error(BTBB_B200_EINVAL, "find_ac_sharded_end: no scan is pending");
-	s->pending = 0;
+	const int g = s->pend_g[0];
+	s->pend_g[0] = s->pend_g[1];
+	s->pending--;
 	int64_t n = 0;
-	int rc = bt_find_ac_dev_end(ctx, &n);      /* waits for the scan + ordering on the scan stream */
+	int rc = bt_find_ac_dev_end(ctx, &n);      /* waits for the oldest pending scan and its ordering pass */
 	*n_local = n;
 	if (rc) return rc;                         /* EOVERFLOW included: the slot is too small for this shard */
-	*g_out = s->gen;
-	s->gen ^= 1;
-	s->last = *g_out; s->n_last = n;
+	*g_out = g;
+	s->last = g; s->n_last = n;
+	s->last_fanned = ctx->last_fanned;
 	return BTBB_B200_OK;
 }
 
@@ -276,6 +299,7 @@ static int shard_push(btbb_b200_ctx *ctx, int g, int64_t n)
 {
 	bt_shard *s = ctx->shard;
 	if (!s->peer) return BTBB_B200_OK;         /* the NCCL form moves the records in _gather */
+	if (s->last_fanned) return BTBB_B200_OK;   /* the ordering kernel has already delivered them */
 	memset(&s->h_hdr[g], 0, sizeof(btbb_b200_hit));
 	s->h_hdr[g].offset = n;
 	BT_CUDA_TRY(cudaMemcpyAsync(s->local[g], &s->h_hdr[g], sizeof(btbb_b200_hit), cudaMemcpyHostToDevice, s->copy));
@@ -371,7 +395,7 @@ extern "C" int btbb_b200_find_ac_sharded_dev(btbb_b200_ctx *ctx, const uint8_t *
 	rc = btbb_b200_find_ac_sharded_end(ctx, &n_local);
 	/* a rank that failed still has to meet the others in the gather; report its error afterwards */
 	const int rc_local = rc;
-	if (rc_local) { s->last = s->gen ^ 1; s->n_last = 0; }
+	if (rc_local) { s->last = s->gen ^ 1; s->n_last = 0; s->last_fanned = 0; }
 	const btbb_b200_hit *slots = NULL;
 	int64_t stride = 0;
 	rc = btbb_b200_find_ac_sharded_gather(ctx, &slots, &stride, counts, n_total);

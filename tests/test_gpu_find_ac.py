@@ -332,3 +332,45 @@ def test_host_entry_point_large_buffer_packs(gpu_ctx2, orc):
         assert rc == -4 and cnt.value == len(want), (env, rc, cnt.value)
         wanted = {r.tobytes() for r in want}
         assert all(r.tobytes() in wanted for r in few) and (np.diff(few["offset"]) > 0).all(), env
+
+
+def test_two_pending_scans_and_tile_kernel_option(gpu_ctx2, orc, product_lib):
+    """Two scans may be pending on one context (_end completes the oldest); a third _begin is refused;
+    the tile-kernel-only option gives the same list as the bulk kernels."""
+    import ctypes as C
+    import torch
+    assert orc.orc_init(2) == 0
+    rng = np.random.default_rng(321)
+    n = 3_000_017
+    s = rng.integers(0, 2, n + 63, dtype=np.uint8)
+    util.plant_syncwords(s, rng, 700, 2)
+    d = torch.from_numpy(s).cuda()
+    cap = 1 << 16
+    ha = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    hb = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    na, nb = n, 1_234_567
+    want_a = util.find_all(orc, "orc", s, na, B.LAP_ANY, 2)
+    want_b = util.find_all(orc, "orc", s, nb, B.LAP_ANY, 1)
+    ctx = gpu_ctx2
+    for _ in range(3):
+        ctx.find_ac_dev_begin(d.data_ptr(), na, ha.data_ptr(), cap, k=2)
+        ctx.find_ac_dev_begin(d.data_ptr(), nb, hb.data_ptr(), cap, k=1)
+        assert product_lib.btbb_b200_find_ac_dev_begin(ctx.h, d.data_ptr(), nb, B.LAP_ANY, 1, hb.data_ptr(), cap, 0) == -1
+        ca, rc = ctx.find_ac_dev_end()
+        assert rc == 0 and ha[:ca].cpu().numpy().tobytes() == want_a.tobytes()
+        cb, rc = ctx.find_ac_dev_end()
+        assert rc == 0 and hb[:cb].cpu().numpy().tobytes() == want_b.tobytes()
+    n_end = C.c_int64(0)
+    assert product_lib.btbb_b200_find_ac_dev_end(ctx.h, C.byref(n_end)) == -1      # nothing pending
+    # a known-LAP scan (generic ordering path) queued behind a promiscuous one
+    lap = int(want_a[0]["lap"])
+    want_k = util.find_all(orc, "orc", s, na, lap, 3)
+    ctx.find_ac_dev_begin(d.data_ptr(), na, ha.data_ptr(), cap, k=2)
+    ctx.find_ac_dev_begin(d.data_ptr(), na, hb.data_ptr(), cap, lap=lap, k=3)
+    ca, rc = ctx.find_ac_dev_end()
+    cb, rc2 = ctx.find_ac_dev_end()
+    assert rc == 0 and rc2 == 0 and ha[:ca].cpu().numpy().tobytes() == want_a.tobytes() and hb[:cb].cpu().numpy().tobytes() == want_k.tobytes()
+    ctx.set_option(B.OPT_TILE_KERNEL_ONLY, 1)
+    ca, rc = ctx.find_ac_dev(d.data_ptr(), na, ha.data_ptr(), cap, k=2)
+    ctx.set_option(B.OPT_TILE_KERNEL_ONLY, 0)
+    assert rc == 0 and ha[:ca].cpu().numpy().tobytes() == want_a.tobytes()
