@@ -98,6 +98,7 @@ extern "C" void btbb_b200_destroy(btbb_b200_ctx *ctx)
 	if (ctx->d_sieve_cur) cudaFree(ctx->d_sieve_cur);
 	for (int i = 0; i < 2; i++) if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
 	if (ctx->d_dec_tables) cudaFree(ctx->d_dec_tables);
+	if (ctx->d_perm_tables) cudaFree(ctx->d_perm_tables);
 	for (int i = 0; i < 4; i++) if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
 	delete ctx->host_lock;
 	if (ctx->ev_reset) cudaEventDestroy(ctx->ev_reset);

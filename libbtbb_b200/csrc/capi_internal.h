@@ -110,6 +110,7 @@ struct btbb_b200_ctx {
 	int64_t *d_sieve_idx;        /* UAP sieve: packets of the current round (sieve_cap entries) */
 	int64_t *d_sieve_cur;        /* UAP sieve: per-piconet cursor, then one 64-bit counter */
 	int64_t sieve_groups_cap;
+	void *d_perm_tables;         /* hop sequence: the factored perm5 tables (hops.cu) */
 	void *d_dec_tables;          /* per-packet chain: device copy of btd_tables (decode_core.h) */
 	void *d_scratch[4];          /* grow-only device scratch of the host-buffer entry points */
 	size_t scratch_cap[4];

@@ -10,11 +10,11 @@
  *
  * Here:
  *   hop_sequence_kernel   the table itself, any index range, one thread per 16 consecutive entries
- *       (one 128-bit store).  Within 64 consecutive entries only the 5-bit permutation INPUT
- *       changes, so the permutation is evaluated bit-sliced: five 32-bit planes (bit z of plane b =
- *       bit b of input z) go through the 14 butterflies as plane swaps selected by the control word,
- *       and an entry reads its five output bits at position z.  No table, ~20 integer operations
- *       per entry; the store stream is the bound.
+ *       (one 128-bit store).  The butterfly network factors by its control bits: the first five
+ *       stages are steered by c (5 bits), the last nine by d (9 bits), so perm5(z, c, d) =
+ *       D[d][C[c][z]] with a 1 KiB and a 16 KiB table (the reference's perm_table is 512 KiB).  Both
+ *       are address-independent, built once per process and staged into shared memory per CTA; an
+ *       entry then costs two table reads, the register-bank read and ~10 integer operations.
  *   hop_winnow_*          hop reversal without the table: all 2^21 CLK1-27 values that agree with the
  *       known CLK1-6 are candidates; each thread walks the observations for one candidate until the
  *       first disagreement (78 of 79 fall at the first), evaluating the hop selection kernel
@@ -46,60 +46,58 @@ __host__ __device__ __forceinline__ uint32_t mod_small(uint32_t v, uint32_t m, u
 	return v - m * ((v * inv) >> 16);
 }
 
-/* stage i of perm5 swaps bits IDX1[i], IDX2[i] when control bit i is set; stages run 13 .. 0,
+/* stage i of perm5 swaps bits i1[i], i2[i] when control bit i is set; stages run 13 .. 0,
  * control = c (5 bits) << 9 | d (9 bits) */
-__device__ __constant__ int c_idx1[14] = {0, 2, 1, 3, 0, 1, 0, 3, 1, 0, 2, 1, 0, 1};
-__device__ __constant__ int c_idx2[14] = {1, 3, 2, 4, 4, 3, 2, 4, 4, 3, 4, 3, 3, 2};
 
-/* the permutation of one control word applied to ALL 32 inputs at once */
-__device__ __forceinline__ void perm5_planes(uint32_t ctrl, uint32_t pl[5])
+/* perm5 (:258-290) for one input, stages [hi, lo] of the butterfly network */
+__host__ __device__ __forceinline__ uint32_t perm5_stages(uint32_t z, uint32_t ctrl, int hi, int lo)
 {
-	pl[0] = 0xAAAAAAAAu; pl[1] = 0xCCCCCCCCu; pl[2] = 0xF0F0F0F0u; pl[3] = 0xFF00FF00u; pl[4] = 0xFFFF0000u;
-	/* unrolled with literal plane indices so that everything stays in registers */
-#define BT_STAGE(i, x, y) { const uint32_t m = 0u - ((ctrl >> (i)) & 1u), t = (pl[x] ^ pl[y]) & m; pl[x] ^= t; pl[y] ^= t; }
-	BT_STAGE(13, 1, 2) BT_STAGE(12, 0, 3) BT_STAGE(11, 1, 3) BT_STAGE(10, 2, 4) BT_STAGE(9, 0, 3)
-	BT_STAGE(8, 1, 4)  BT_STAGE(7, 3, 4)  BT_STAGE(6, 0, 2)  BT_STAGE(5, 1, 3)  BT_STAGE(4, 0, 4)
-	BT_STAGE(3, 3, 4)  BT_STAGE(2, 1, 2)  BT_STAGE(1, 2, 3)  BT_STAGE(0, 0, 1)
-#undef BT_STAGE
+	const int i1[14] = {0, 2, 1, 3, 0, 1, 0, 3, 1, 0, 2, 1, 0, 1};
+	const int i2[14] = {1, 3, 2, 4, 4, 3, 2, 4, 4, 3, 4, 3, 3, 2};
+	for (int i = hi; i >= lo; i--) {
+		const uint32_t t = ((z >> i1[i]) ^ (z >> i2[i])) & (ctrl >> i) & 1u;
+		z ^= (t << i1[i]) | (t << i2[i]);
+	}
+	return z;
 }
 
-__device__ __forceinline__ uint32_t planes_at(const uint32_t pl[5], uint32_t z)
-{
-	return ((pl[0] >> z) & 1u) | (((pl[1] >> z) & 1u) << 1) | (((pl[2] >> z) & 1u) << 2) |
-	       (((pl[3] >> z) & 1u) << 3) | (((pl[4] >> z) & 1u) << 4);
-}
+/* C[c][z]: stages 13..9 under control c; D[d][z]: stages 8..0 under control d */
+struct perm_tables { uint8_t c[32 * 32]; uint8_t d[512 * 32]; };
+constexpr int PERM_BYTES = (int)sizeof(perm_tables);
+static_assert(PERM_BYTES % 16 == 0, "perm tables are copied as 128-bit words");
 
 /* sequence entries [16 q, 16 q + 16): x = 8 (q & 3) .. + 7, both values of clock bit 1 */
-__device__ __forceinline__ void hop16(const hop_consts &h, const uint8_t *s_bank, uint32_t q, uint8_t out[16])
+__device__ __forceinline__ void hop16(const hop_consts &h, const uint8_t *s_bank, const perm_tables *pt, uint32_t q, uint8_t out[16])
 {
 	const uint32_t kk = q >> 2;                       /* index >> 6: the (h, i, j, k) tuple */
 	const uint32_t a = (uint32_t)h.a1 ^ ((q >> 16) & 31u);
 	const uint32_t c = (uint32_t)h.c1 ^ ((q >> 11) & 31u);
 	const uint32_t d = (uint32_t)h.d1 ^ (kk & 511u);
 	const uint32_t f = (16u * (kk & 0x1fffffu)) % 79u;
-	uint32_t p0[5], p1[5];
-	perm5_planes((c << 9) | d, p0);
-	perm5_planes(((c ^ 31u) << 9) | d, p1);
+	const uint8_t *c0 = pt->c + 32 * c, *c1 = pt->c + 32 * (c ^ 31u), *dd = pt->d + 32 * d;
 	const uint32_t base = (uint32_t)h.e + (h.afh ? mod_small(f, (uint32_t)h.used, h.inv) : f);
 	#pragma unroll
 	for (int t = 0; t < 8; t++) {
 		const uint32_t x = 8u * (q & 3u) + (uint32_t)t;
 		const uint32_t z = ((x + a) & 31u) ^ (uint32_t)h.b;
-		out[2 * t] = s_bank[mod_small(planes_at(p0, z) + base, (uint32_t)h.used, h.inv)];
-		out[2 * t + 1] = s_bank[mod_small(planes_at(p1, z) + base + 32u, (uint32_t)h.used, h.inv)];
+		out[2 * t] = s_bank[mod_small(dd[c0[z]] + base, (uint32_t)h.used, h.inv)];
+		out[2 * t + 1] = s_bank[mod_small(dd[c1[z]] + base + 32u, (uint32_t)h.used, h.inv)];
 	}
 }
 
-__global__ void __launch_bounds__(256) hop_sequence_kernel(hop_consts h, int64_t first, int64_t n, uint8_t *out)
+__global__ void __launch_bounds__(256) hop_sequence_kernel(hop_consts h, const perm_tables *g_pt, int64_t first, int64_t n, uint8_t *out)
 {
 	__shared__ uint8_t s_bank[80];
+	__shared__ __align__(16) perm_tables s_pt;
 	if (threadIdx.x < 80) s_bank[threadIdx.x] = h.bank[threadIdx.x];
+	for (int i = threadIdx.x; i < PERM_BYTES / 16; i += blockDim.x)
+		reinterpret_cast<uint4 *>(&s_pt)[i] = reinterpret_cast<const uint4 *>(g_pt)[i];
 	__syncthreads();
 	const int64_t q0 = first >> 4, q1 = (first + n + 15) >> 4;
 	const bool aligned = ((reinterpret_cast<uintptr_t>(out) - (uintptr_t)first) & 15) == 0;
 	for (int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (int64_t)gridDim.x * blockDim.x) {
 		union { uint8_t b[16]; uint4 v; } u;
-		hop16(h, s_bank, (uint32_t)q & (SEQ_MASK >> 4), u.b);
+		hop16(h, s_bank, &s_pt, (uint32_t)q & (SEQ_MASK >> 4), u.b);
 		const int64_t i0 = 16 * q;
 		if (aligned && i0 >= first && i0 + 16 <= first + n)
 			*reinterpret_cast<uint4 *>(out + (i0 - first)) = u.v;
@@ -118,12 +116,7 @@ __device__ __forceinline__ uint32_t hop_one(const hop_consts &h, const uint8_t *
 	const uint32_t c = ((uint32_t)h.c1 ^ ((pair >> 14) & 31u)) ^ (y1 ? 31u : 0u);
 	const uint32_t d = (uint32_t)h.d1 ^ (kk & 511u);
 	const uint32_t ctrl = (c << 9) | d;
-	uint32_t z = ((x + a) & 31u) ^ (uint32_t)h.b;
-	#pragma unroll
-	for (int i = 13; i >= 0; i--) {
-		const uint32_t t = ((z >> c_idx1[i]) ^ (z >> c_idx2[i])) & (ctrl >> i) & 1u;
-		z ^= (t << c_idx1[i]) | (t << c_idx2[i]);
-	}
+	const uint32_t z = perm5_stages(((x + a) & 31u) ^ (uint32_t)h.b, ctrl, 13, 0);
 	const uint32_t f = (16u * kk) % 79u;
 	const uint32_t v = z + (uint32_t)h.e + (h.afh ? mod_small(f, (uint32_t)h.used, h.inv) : f) + 32u * y1;
 	uint32_t ch = s_bank[mod_small(v, (uint32_t)h.used, h.inv)];
@@ -255,9 +248,22 @@ extern "C" int btbb_b200_hop_sequence_dev(btbb_b200_ctx *ctx, const btbb_b200_ho
 	BT_CUDA_TRY(cudaSetDevice(ctx->device));
 	const int64_t chunks = ((first + n + 15) >> 4) - (first >> 4);
 	int64_t blocks = (chunks + 255) / 256;
-	const int64_t cap = (int64_t)ctx->sm_count * 16;
+	const int64_t cap = (int64_t)ctx->sm_count * 8;
 	if (blocks > cap) blocks = cap;
-	hop_sequence_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(h, first, n, d_out);
+	if (!ctx->d_perm_tables) {
+		perm_tables *t = new perm_tables;
+		for (uint32_t c = 0; c < 32; c++)
+			for (uint32_t z = 0; z < 32; z++) t->c[32 * c + z] = (uint8_t)perm5_stages(z, c << 9, 13, 9);
+		for (uint32_t d = 0; d < 512; d++)
+			for (uint32_t z = 0; z < 32; z++) t->d[32 * d + z] = (uint8_t)perm5_stages(z, d, 8, 0);
+		void *dp = NULL;
+		cudaError_t e = cudaMalloc(&dp, sizeof(perm_tables));
+		if (e == cudaSuccess) e = cudaMemcpy(dp, t, sizeof(perm_tables), cudaMemcpyHostToDevice);
+		delete t;
+		if (e != cudaSuccess) { if (dp) cudaFree(dp); return btbb_b200_cuda_fail(e, "hop_sequence: permutation tables"); }
+		ctx->d_perm_tables = dp;
+	}
+	hop_sequence_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(h, static_cast<const perm_tables *>(ctx->d_perm_tables), first, n, d_out);
 	BT_CUDA_TRY(cudaGetLastError());
 	return BTBB_B200_OK;
 }

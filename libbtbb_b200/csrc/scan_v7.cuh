@@ -377,9 +377,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 		if (M2G == 2 && WIN == 0) {
 			/* Global first-level map: a probe is an L2 round trip, so the slots run in two phases.
 			 * A: window + syndrome value of every in-place candidate, parked in a lane-private
-			 * column of the (otherwise unused) map area of shared memory.  B: per pair of rows,
-			 * all ten probes are issued back to back and only then looked at; the candidate bits
-			 * are enumerated a second time instead of being stored. */
+			 * column of the (otherwise unused) map area of shared memory. */
 			static_assert(M2G != 2 || NSLOTS * K <= 20, "parking area holds 20 values per lane");
 			uint32_t c0[K];
 			#pragma unroll
@@ -396,29 +394,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) scan_promisc_v7(const args a)
 					sts32(j < 16 ? pend_a + 128 * j : pend_b + 128 * (j - 16), sy);
 				}
 			}
-			#pragma unroll
-			for (int h = 0; h < K; h += 2) {
-				uint32_t sy[2][NSLOTS], bb[2][NSLOTS], v[2][NSLOTS];
+			/* B: all NSLOTS * K probes of the lane are issued back to back (one byte load each, an L2
+			 * round trip), then looked at: the syndrome values come back from the parking area and the
+			 * candidate bits are enumerated a second time instead of being kept in registers */
+			uint32_t v[K][NSLOTS];
+			{
+				uint32_t c1[K];
+				#pragma unroll
+				for (int k = 0; k < K; k++) c1[k] = c0[k];
 				#pragma unroll
 				for (int t = 0; t < NSLOTS; t++) {
 					#pragma unroll
-					for (int kk = 0; kk < 2; kk++) {
-						const int j = t * K + h + kk;
-						sy[kk][t] = lds32(j < 16 ? pend_a + 128 * j : pend_b + 128 * (j - 16));
-						bb[kk][t] = onebit(bfind(c0[h + kk]));
-						c0[h + kk] = mad_lo(bb[kk][t], m1, c0[h + kk]);
-						v[kk][t] = 0;
-						if (bb[kk][t])
-							asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v[kk][t]) : "l"(gm.p + (sy[kk][t] >> gm.shift)));
+					for (int k = 0; k < K; k++) {
+						const int j = t * K + k;
+						const uint32_t sy = lds32(j < 16 ? pend_a + 128 * j : pend_b + 128 * (j - 16));
+						const uint32_t b1 = onebit(bfind(c1[k]));
+						c1[k] = mad_lo(b1, m1, c1[k]);
+						v[k][t] = 0;
+						if (b1)
+							asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v[k][t]) : "l"(gm.p + (sy >> gm.shift)));
 					}
 				}
+			}
+			#pragma unroll
+			for (int t = 0; t < NSLOTS; t++) {
 				#pragma unroll
-				for (int t = 0; t < NSLOTS; t++) {
-					#pragma unroll
-					for (int kk = 0; kk < 2; kk++) {
-						const uint32_t x = (mul_lo(v[kk][t], 0x01010101u) >> (sy[kk][t] & 31)) & 1u;
-						hitm[h + kk] = mad_lo(x, bb[kk][t], hitm[h + kk]);
-					}
+				for (int k = 0; k < K; k++) {
+					const int j = t * K + k;
+					const uint32_t sy = lds32(j < 16 ? pend_a + 128 * j : pend_b + 128 * (j - 16));
+					const uint32_t b1 = onebit(bfind(c0[k]));
+					c0[k] = mad_lo(b1, m1, c0[k]);
+					const uint32_t x = (mul_lo(v[k][t], 0x01010101u) >> (sy & 31)) & 1u;
+					hitm[k] = mad_lo(x, b1, hitm[k]);
 				}
 			}
 		} else {

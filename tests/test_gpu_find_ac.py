@@ -225,8 +225,8 @@ def test_packed_ingest_matches_oracle(gpu_ctx2, orc, n):
 
 
 def test_begin_end_halves_and_offset_bias(gpu_ctx2, orc):
-    """btbb_b200_find_ac_dev == _begin + _end; the offset bias shifts every reported offset; one
-    pending call per context."""
+    """btbb_b200_find_ac_dev == _begin + _end; the offset bias shifts every reported offset (also on the
+    generic ordering path with a bias that makes the offsets straddle a power of two)."""
     import torch
     assert orc.orc_init(2) == 0
     rng = np.random.default_rng(4242)
@@ -240,8 +240,6 @@ def test_begin_end_halves_and_offset_bias(gpu_ctx2, orc):
     for lap in (B.LAP_ANY, int(want[0]["lap"])):
         ref = want if lap == B.LAP_ANY else util.find_all(orc, "orc", s, n, lap, 2)
         gpu_ctx2.find_ac_dev_begin(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=lap, k=2)
-        with pytest.raises(B.BtbbError):
-            gpu_ctx2.find_ac_dev_begin(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=lap, k=2)
         cnt, rc = gpu_ctx2.find_ac_dev_end()
         assert rc == 0 and d_hits[:cnt].cpu().numpy().tobytes() == ref.tobytes()
     with pytest.raises(B.BtbbError):
@@ -256,6 +254,15 @@ def test_begin_end_halves_and_offset_bias(gpu_ctx2, orc):
         assert got.tobytes() == want.tobytes()
         h = gpu_ctx2.find_ac_host(s, n, B.LAP_ANY, 2)   # the host entry point is not biased
         assert h.tobytes() == want.tobytes()
+        # known LAP takes the radix-sort path: digits are taken from offset - bias (a bias that
+        # carries the offsets across 2^18 / 2^27 used to wrap the low digits)
+        lap = int(want[0]["lap"])
+        ref = util.find_all(orc, "orc", s, n, lap, 4)
+        for bias in ((1 << 18) - 1000, (1 << 27) - n // 2, 10**11 + 7, -(n // 3)):
+            gpu_ctx2.set_offset_bias(bias)
+            cnt, rc = gpu_ctx2.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=lap, k=4)
+            got = d_hits[:cnt].cpu().numpy().reshape(-1).view(B.HIT_DTYPE).copy()
+            assert rc == 0 and np.array_equal(got["offset"], ref["offset"] + bias), bias
     finally:
         gpu_ctx2.set_offset_bias(0)
 

@@ -3,8 +3,9 @@
     ncu --set full -k regex:<kernel> -c 1 ... python tools/ncu_targets.py <target>
 
 targets: v7 (promiscuous k=2), k3 / k4 / k5 (larger error tables), known (known-LAP scan),
-decode0 (btbb_decode with the true clock), decode1 (64-clock sweep, full records), tc16 + sieve
-(UAP sieve: compact sweep + candidate elimination)."""
+decode0 (btbb_decode with the true clock), decode1 (64-clock sweep, full records), tc16 (compact
+64-clock sweep), sieve (UAP sieve: compact sweep + candidate elimination), hops (2^27-entry hop
+sequence + a winnow call)."""
 import ctypes as C
 import os
 import sys
@@ -19,7 +20,16 @@ target = sys.argv[1]
 lib = B.lib()
 st = torch.cuda.current_stream().cuda_stream
 reps = int(os.environ.get("NCU_REPS", "2"))
-if target in ("v7", "k3", "k4", "k5", "known"):
+if target == "hops":
+    ctx = B.Context(0, 0)
+    d = torch.empty(1 << 27, dtype=torch.uint8, device="cuda")
+    cfg = B.hop_cfg(0xA96EF25)
+    for _ in range(reps):
+        B.check(lib.btbb_b200_hop_sequence_dev(ctx.h, C.byref(cfg), 0, 1 << 27, d.data_ptr(), st))
+    torch.cuda.synchronize()
+    c, a = B.hop_winnow(ctx, cfg, 5, np.arange(12) * 7, np.arange(12) % 79)
+    print("hops done", len(c))
+elif target in ("v7", "k3", "k4", "k5", "known"):
     n = int(float(os.environ.get("NCU_SYMBOLS", "4e9")))
     k = {"v7": 2, "k3": 3, "k4": 4, "k5": 5, "known": 2}[target]
     cfg = B.synth_cfg(n + 72, stride=10000, mix=("ID", "DM1", "DM3", "DH1", "FHS"))
@@ -71,14 +81,16 @@ else:
     if coherent:
         pk.view(torch.int32)[:, 3] = slot.to(torch.int32)
         pk.view(torch.int32)[:, 5] = (slot % 79).to(torch.int32)
-        states = torch.zeros((len(laps), 160), dtype=torch.uint8, device="cuda")
-        for _ in range(reps):
-            states.zero_()
-            B.check(lib.btbb_b200_uap_sieve_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, gs.data_ptr(), len(laps),
-                                                 states.data_ptr(), None, st))
-        d_tc = torch.zeros(cnt * 64, dtype=torch.int16, device="cuda")
-        for _ in range(reps):
-            B.check(lib.btbb_b200_try_clocks_compact_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, d_tc.data_ptr(), st))
+        if target == "sieve":
+            states = torch.zeros((len(laps), 160), dtype=torch.uint8, device="cuda")
+            for _ in range(reps):
+                states.zero_()
+                B.check(lib.btbb_b200_uap_sieve_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, gs.data_ptr(), len(laps),
+                                                     states.data_ptr(), None, st))
+        else:
+            d_tc = torch.zeros(cnt * 64, dtype=torch.int16, device="cuda")
+            for _ in range(reps):
+                B.check(lib.btbb_b200_try_clocks_compact_dev(ctx.h, d.data_ptr(), n + 63, pk.data_ptr(), cnt, d_tc.data_ptr(), st))
     else:
         t = d_truth[torch.clamp(slot, max=n_slots - 1)]
         pk.view(torch.int32)[:, 3] = t[:, 0]
