@@ -131,9 +131,10 @@ __global__ void __launch_bounds__(WIN_BLOCK) hop_winnow_kernel(hop_consts h, uin
 							       unsigned int *block_count)
 {
 	__shared__ uint8_t s_bank[80];
-	__shared__ unsigned int s_cnt;
+	__shared__ unsigned int s_cnt, s_hist[64];      /* nearly every candidate falls at one of the first observations */
 	if (threadIdx.x < 80) s_bank[threadIdx.x] = h.bank[threadIdx.x];
 	if (threadIdx.x == 0) s_cnt = 0;
+	if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
 	__syncthreads();
 	const uint32_t t = blockIdx.x * WIN_BLOCK + threadIdx.x;
 	const uint32_t cand = known6 + 64u * t;
@@ -141,10 +142,12 @@ __global__ void __launch_bounds__(WIN_BLOCK) hop_winnow_kernel(hop_consts h, uin
 	for (; m < n_obs; m++)
 		if (hop_one(h, s_bank, (cand + (uint32_t)idx[m]) & SEQ_MASK) != chan[m]) break;
 	first_fail[t] = (uint16_t)m;
-	if (m < n_obs) atomicAdd(&fail_hist[m], 1u);
-	else atomicAdd(&s_cnt, 1u);
+	if (m >= n_obs) atomicAdd(&s_cnt, 1u);
+	else if (m < 64) atomicAdd(&s_hist[m], 1u);
+	else atomicAdd(&fail_hist[m], 1u);
 	__syncthreads();
 	if (threadIdx.x == 0) block_count[blockIdx.x] = s_cnt;
+	if (threadIdx.x < 64 && threadIdx.x < n_obs && s_hist[threadIdx.x]) atomicAdd(&fail_hist[threadIdx.x], s_hist[threadIdx.x]);
 }
 
 /* exclusive scan of the per-block survivor counts (one block), total in *total */
