@@ -475,6 +475,19 @@ static int unpack_to_bytes(btbb_b200_ctx *ctx, const uint32_t *d_words, int64_t 
 	return BTBB_B200_OK;
 }
 
+/* What a scan needs set up in device memory before its kernels run -- the exact test's parameter block
+ * and zeroed counters -- done by one small kernel instead of a host-to-device copy and two memsets:
+ * nothing on a scan's stream then needs a copy engine, which the multi-GPU exchange keeps busy with
+ * peer-to-peer copies of hit records (a 128-byte parameter copy queued behind eight 16 MB pushes was
+ * what held back the next scan on 8 GPUs). */
+__global__ void __launch_bounds__(256) scan_prep_kernel(sc::xparams xp, sc::xparams *slot, uint32_t *zero_a, int na,
+							 unsigned long long *zero_b, int nb)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0) *slot = xp;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na; i += gridDim.x * blockDim.x) zero_a[i] = 0;
+	if (blockIdx.x == 0 && threadIdx.x < nb) zero_b[threadIdx.x] = 0;
+}
+
 /*
  * Dispatcher.  Every whole 4096-symbol strip that starts on a 32-byte boundary goes through a bulk
  * kernel -- scan_v7.cuh for promiscuous scans (its map hierarchy depends on the error tables the
@@ -502,6 +515,7 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	const bool k3 = !known && ctx->table_k >= 3;      /* second (3 errors) or first (4 / 5) map level in global memory */
 	const bool k45 = !known && ctx->table_k >= 4;
 	if (ctx->opt_tile_only || (known && k > 16) || (packed && n - 1 < sc::STRIP)) {
+		if (slab) BT_CUDA_TRY(cudaMemsetAsync(d_count, 0, 2 * sizeof(unsigned long long), st));
 		if (packed) {      /* no bulk kernel for this case: expand to the byte format and take the tile kernel */
 			int rc0 = unpack_to_bytes(ctx, reinterpret_cast<const uint32_t *>(d_stream), 0, n + 63, st);
 			if (rc0) return rc0;
@@ -517,8 +531,10 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 	 * 2^31 symbols per warp (148 x 32 warps -> ~10^13 symbols); beyond that the tail kernel
 	 * below simply takes the rest */
 	if (nstrips > ((int64_t)1 << 31) / sc::STRIP * 4096) nstrips = ((int64_t)1 << 31) / sc::STRIP * 4096;
-	if (nstrips < 1)      /* (never with packed input: checked above) */
+	if (nstrips < 1) {    /* (never with packed input: checked above) */
+		if (slab) BT_CUDA_TRY(cudaMemsetAsync(d_count, 0, 2 * sizeof(unsigned long long), st));
 		return scan_launch_v1(ctx, d_stream, n, lap, k, d_out, max_hits, d_count, bias, st);
+	}
 	const int64_t body_end = head + nstrips * sc::STRIP;
 	/* packed input: the tile kernel takes the ragged tail from an expanded copy */
 	const uint8_t *d_tail = d_stream + body_end;
@@ -542,7 +558,6 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		const int nw = (int)grid * bulk_warps;
 		int rc2 = bt_ensure_slab(ctx, nw + 2);
 		if (rc2) return rc2;
-		BT_CUDA_TRY(cudaMemsetAsync(ctx->d_slab_cnt, 0, (size_t)(nw + 2) * sizeof(uint32_t) + 2 * sizeof(unsigned long long), st));
 		xp.slab = ctx->d_slab; xp.slab_cnt = ctx->d_slab_cnt; xp.slab_cap = BT_SLAB_CAP;
 		slab->used = 1; slab->nw = nw;
 	}
@@ -550,7 +565,13 @@ int bt_scan_launch_ex(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t n, ui
 		BT_CUDA_TRY(cudaMalloc(&ctx->d_xp, 16 * 128));
 	static_assert(sizeof(sc::xparams) <= 128, "xparams slot");
 	void *slot = (char *)ctx->d_xp + 128 * (ctx->xp_next++ & 15);
-	BT_CUDA_TRY(cudaMemcpyAsync(slot, &xp, sizeof(xp), cudaMemcpyHostToDevice, st));
+	{
+		/* slab mode: the per-slab fill counts and the two 64-bit edge counters behind them, plus the
+		 * context's hit counter pair (the caller's d_count) */
+		const int na = slab_mode ? ((slab->nw + 2 + 1) & ~1) + 4 : 0;
+		scan_prep_kernel<<<slab_mode ? 8 : 1, 256, 0, st>>>(xp, static_cast<sc::xparams *>(slot), ctx->d_slab_cnt, na,
+								   slab_mode ? d_count : NULL, slab_mode ? 2 : 0);
+	}
 	if (known) {
 		/* known LAP: bit-sliced prefilter on 16 sync-word bits that are all 0 (or all 1) */
 		vk::args a;
@@ -683,6 +704,7 @@ namespace {
  * bases (64-bit) into base[0..nw+2), the total into out[0] and an overflow flag into out[1]. */
 __global__ void __launch_bounds__(1024) slab_scan_kernel(uint32_t *cnt, const unsigned long long *edge, int nw,
 							 unsigned long long *base, unsigned long long *out,
+							 volatile unsigned long long *host_out,
 							 btbb_b200_hit *const *fan, int fan_n)
 {
 	__shared__ unsigned long long wsum[32];
@@ -732,7 +754,12 @@ __global__ void __launch_bounds__(1024) slab_scan_kernel(uint32_t *cnt, const un
 		if (t == 1023) carry_s = excl + x;
 		__syncthreads();
 	}
-	if (t == 0) { out[0] = carry_s; out[1] = (unsigned long long)over; }
+	if (t == 0) {
+		out[0] = carry_s; out[1] = (unsigned long long)over;
+		/* the same two words straight into pinned host memory (no device-to-host copy on the stream) */
+		host_out[0] = carry_s; host_out[1] = (unsigned long long)over;
+		__threadfence_system();
+	}
 	/* fan-out (multi-GPU): the record in front of every destination list is its header, the hit count */
 	if (t < fan_n) {
 		btbb_b200_hit hdr;
@@ -952,14 +979,14 @@ static int find_ac_begin_lane(btbb_b200_ctx *ctx, const uint8_t *d_stream, int p
 	if (lap != BTBB_B200_LAP_ANY) return BTBB_B200_OK;       /* known LAP: the generic path, in end() */
 	/* fast ordering: per-warp slabs, one small sort per slab (promiscuous bulk path only) */
 	bt_slab_req req;
-	cudaError_t e = cudaMemsetAsync(ctx->d_count, 0, 2 * sizeof(unsigned long long), st);
-	if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "cudaMemsetAsync(find_ac counters)"); }
+	cudaError_t e = cudaSuccess;
+	/* (bt_scan_launch_ex zeroes the counters: in the bulk path's set-up kernel, else with a memset) */
 	rc = bt_scan_launch_ex(ctx, d_stream, search_length, lap, max_ac_errors, ctx->d_tmp, max_hits, ctx->d_count, pd.bias, st, &req, packed);
 	if (rc) { pd.mode = BT_PENDING_NONE; return rc; }
 	if (req.used) {
 		const int nw = req.nw;
 		unsigned long long *edge_cnt = (unsigned long long *)(ctx->d_slab_cnt + ((nw + 2 + 1) & ~1));
-		slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count, ctx->d_fan, ctx->fan_n);
+		slab_scan_kernel<<<1, 1024, 0, st>>>(ctx->d_slab_cnt, edge_cnt, nw, ctx->d_slab_base, ctx->d_count, ctx->h_res, ctx->d_fan, ctx->fan_n);
 		/* the sort is safe to run even if a slab overflowed (counts are clamped); its output is
 		 * then simply not used */
 		slab_sort_kernel<<<nw + 2, 256, 0, st>>>(ctx->d_slab, ctx->d_slab_cnt, ctx->d_slab_base, d_hits, max_hits, ctx->d_fan, ctx->fan_n);
@@ -967,7 +994,9 @@ static int find_ac_begin_lane(btbb_b200_ctx *ctx, const uint8_t *d_stream, int p
 		pd.mode = BT_PENDING_SLAB;
 	} else
 		pd.mode = BT_PENDING_UNORDERED;      /* the unordered list is in d_tmp, its length in d_count[0] */
-	e = cudaMemcpyAsync(ctx->h_res, ctx->d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+	/* slab mode: slab_scan_kernel has stored the counters into the pinned host words itself */
+	if (pd.mode != BT_PENDING_SLAB)
+		e = cudaMemcpyAsync(ctx->h_res, ctx->d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done, st);
 	if (e == cudaSuccess) e = cudaGetLastError();
 	if (e != cudaSuccess) { pd.mode = BT_PENDING_NONE; return btbb_b200_cuda_fail(e, "find_ac: enqueue"); }
