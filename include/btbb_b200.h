@@ -281,9 +281,9 @@ int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t str
  * seam overlap at 72); the kernels report GLOBAL offsets.  Ranges partition the positions, so the
  * rank-order concatenation of the per-rank sorted lists is the sorted list of the whole stream.
  * The records travel over NVLink peer memory: every rank's gather buffer is mapped into every other
- * rank (CUDA IPC); after a scan its records are pushed into this rank's slot on every GPU by the copy
- * engines, underneath the next scan (or, BTBB_B200_SHARD_FUSED_STORES, stored there by the kernel that
- * orders the hits).  With BTBB_B200_SHARD_NCCL_ONLY, or where peer mapping fails, the exchange is an
+ * rank (CUDA IPC) and the kernel that orders a scan's hits stores each record into this rank's slot on
+ * all GPUs as it writes the local list -- the all-gather is fused into the ordering pass (or,
+ * BTBB_B200_SHARD_COPY_ENGINES, pushed there by the copy engines afterwards).  With BTBB_B200_SHARD_NCCL_ONLY, or where peer mapping fails, the exchange is an
  * NCCL allgatherv (one all-gather of the counts + one group of exact-size broadcasts).  NCCL (libnccl.so.2) is loaded on first use.
  *
  *   rank 0:      btbb_b200_shard_unique_id(id); hand the 128 bytes to every rank (any transport)
@@ -298,8 +298,7 @@ int btbb_b200_uap_sieve_host(btbb_b200_ctx *ctx, const char *stream, int64_t str
  */
 #define BTBB_B200_SHARD_ID_BYTES 128
 #define BTBB_B200_SHARD_NCCL_ONLY 1       /* exchange = NCCL allgatherv after each scan */
-#define BTBB_B200_SHARD_COPY_ENGINES 2    /* (the default) peer memory, pushed by the copy engines underneath the next scan */
-#define BTBB_B200_SHARD_FUSED_STORES 4    /* peer memory, stored by the kernel that orders the hits (no copies; NVLink time inside the ordering pass) */
+#define BTBB_B200_SHARD_COPY_ENGINES 2    /* peer memory, pushed by the copy engines while the next scan runs, instead of stored by the ordering kernel */
 int btbb_b200_shard_unique_id(void *id);
 int btbb_b200_shard_init(btbb_b200_ctx *ctx, const void *id, int rank, int world, int64_t slot_records, int flags);
 int btbb_b200_shard_info(const btbb_b200_ctx *ctx, int *rank, int *world, int *peer_memory);

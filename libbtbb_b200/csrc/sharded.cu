@@ -10,21 +10,20 @@
  * of the per-rank sorted lists is the globally sorted list the reference's iteration produces.
  *
  * Two forms of the exchange:
- *   peer memory, copy engines (default)  every rank owns a gather buffer of world slots x 2
- *       generations, mapped into every peer with CUDA IPC.  After its scan a rank pushes [count
- *       header | records] into its slot on every peer with device-to-device copies on a copy stream
- *       that never waits for the scan stream.  The scan kernel holds every SM (one persistent CTA per
- *       SM), so copy engines are the only thing that can run beside it: NVLink moves the records
- *       (16 MB per rank and peer at the bench's hit density) underneath the NEXT scan, which is
- *       already queued (two scans may be pending).  For this to overlap, nothing on the scan's own
- *       stream may need a copy engine: its parameter block and counters are set up by a kernel and
- *       its counters are read back through pinned host memory (find_ac.cu).
- *   peer memory, fused stores (BTBB_B200_SHARD_FUSED_STORES)  the ordering kernel (slab_sort_kernel)
- *       stores every record it places also into this rank's slot on EVERY GPU -- plain stores to peer
- *       memory over NVLink -- and slab_scan_kernel writes the count header the same way: no copy
- *       descriptors, no host call, complete when the scan's stream is.  The NVLink time is then part
- *       of the ordering pass (0.16 ms for 112 MB at 8 GPUs) instead of hidden under the next scan:
- *       the right form for sparse hit lists or un-pipelined callers.
+ *   peer memory, fused stores (default)  every rank owns a gather buffer of world slots x 2
+ *       generations, mapped into every peer with CUDA IPC.  The ordering kernel of a scan
+ *       (slab_sort_kernel, find_ac.cu) stores every record it places not only into the local list but
+ *       also into this rank's slot on EVERY GPU -- plain stores to peer memory over NVLink -- and
+ *       slab_scan_kernel writes the count header the same way: the all-gather is fused into the
+ *       ordering pass, costs no launch, no copy descriptor and no host call, and is complete when the
+ *       scan's stream is.
+ *   peer memory, copy engines (BTBB_B200_SHARD_COPY_ENGINES; also the fallback for scans off the slab
+ *       path: known LAP, very dense hits)  [count header | records] pushed into the slot on every peer
+ *       with device-to-device copies on a copy stream that never waits for the scan stream, while the
+ *       next scan (already queued: two may be pending) runs.  Nothing on a scan's own stream needs a
+ *       copy engine (set-up by a kernel, counters through pinned host memory, find_ac.cu).
+ *   Measured on 8 B200 at the bench's hit density (10^6 hits = 16 MB per rank and step, 112 MB in and
+ *   112 MB out per GPU over NVLink): both forms cost the same, ~0.1 ms per 2.1 ms step.
  *   NCCL allgatherv         one ncclAllGather of the counts, then one group of ncclBroadcasts with
  *       exact sizes (NCCL has no native allgatherv).  Needs SMs, so it runs after the scan.
  * NCCL is loaded with dlopen (libnccl.so.2: the copy already in the process when the caller is a
@@ -269,9 +268,9 @@ extern "C" int btbb_b200_find_ac_sharded_begin(btbb_b200_ctx *ctx, const uint8_t
 	if (s->sent_valid[g]) BT_CUDA_TRY(cudaEventSynchronize(s->sent[g]));
 	const int64_t saved = ctx->hit_bias;
 	ctx->hit_bias = first_position;
-	/* BTBB_B200_SHARD_FUSED_STORES: the ordering kernel stores every record into this rank's slot on every GPU
-	 * as it writes the sorted list (promiscuous bulk path; other paths fall back to the copy-engine push in _end) */
-	if (s->peer && (s->flags & BTBB_B200_SHARD_FUSED_STORES)) { ctx->d_fan = s->d_fan[g]; ctx->fan_n = s->world; }
+	/* default: the ordering kernel stores every record into this rank's slot on every GPU as it writes the sorted
+	 * list (promiscuous bulk path; other paths, and BTBB_B200_SHARD_COPY_ENGINES, push with the copy engines in _end) */
+	if (s->peer && !(s->flags & BTBB_B200_SHARD_COPY_ENGINES)) { ctx->d_fan = s->d_fan[g]; ctx->fan_n = s->world; }
 	int rc = bt_find_ac_dev_begin(ctx, d_stream, 0, search_length, lap, max_ac_errors, s->local[g] + 1, s->slot, (cudaStream_t)cuda_stream);
 	ctx->d_fan = NULL; ctx->fan_n = 0;
 	ctx->hit_bias = saved;

@@ -159,7 +159,7 @@ class ShardedScan:
     rank 0 to the others; the scan, the peer-memory exchange and the NCCL allgatherv form all live
     in the library."""
 
-    def __init__(self, ctx, slot_records, group=None, nccl_only=False, fused=False):
+    def __init__(self, ctx, slot_records, group=None, nccl_only=False, copy_engines=False):
         import ctypes as C
         from . import binding as B
         self.B, self.C, self.ctx = B, C, ctx
@@ -177,8 +177,8 @@ class ShardedScan:
             dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if hasattr(dist, "get_global_rank") else 0, group=self.group)
             ident = t.cpu()
         raw = (C.c_uint8 * 128)(*ident.tolist())
-        B.check(B.lib().btbb_b200_shard_init(ctx.h, raw, self.rank, self.world, int(slot_records), (1 if nccl_only else 0) | (4 if fused else 0)))
-        self.fused = bool(fused)
+        B.check(B.lib().btbb_b200_shard_init(ctx.h, raw, self.rank, self.world, int(slot_records), (1 if nccl_only else 0) | (2 if copy_engines else 0)))
+        self.copy_engines = bool(copy_engines)
         pm = C.c_int(0)
         B.check(B.lib().btbb_b200_shard_info(ctx.h, None, None, C.byref(pm)))
         self.peer_memory = bool(pm.value)

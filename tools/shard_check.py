@@ -44,7 +44,7 @@ for lap, k, stride in ((B.LAP_ANY, 2, 4000), (0x9E8B33, 1, 4000)):
     torch.cuda.synchronize()
     assert torch.equal(d_shard, d_whole[rb:rs])
     for nccl_only, ce in ((False, False), (False, True), (True, False)):
-        sh = sharding.ShardedScan(ctx, cap, nccl_only=nccl_only, fused=ce)
+        sh = sharding.ShardedScan(ctx, cap, nccl_only=nccl_only, copy_engines=ce)
         d_all = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
         counts, n_all, rc = sh.scan_all(d_shard.data_ptr(), e - b, b, d_all.data_ptr(), cap, lap=lap, k=k)
         assert rc == 0 and n_all == n_ref, (n_all, n_ref)
@@ -66,7 +66,7 @@ for lap, k, stride in ((B.LAP_ANY, 2, 4000), (0x9E8B33, 1, 4000)):
             slot = torch.as_tensor(_Raw(), device="cuda")[:counts2[r]]
             assert torch.equal(slot, d_ref[at:at + counts2[r]]), f"slot {r} differs"
             at += counts2[r]
-        res[f"lap={lap:#x} k={k} nccl_only={nccl_only} fused={ce}"] = {"hits": n_all, "counts": counts, "peer_memory": sh.peer_memory}
+        res[f"lap={lap:#x} k={k} nccl_only={nccl_only} copy_engines={ce}"] = {"hits": n_all, "counts": counts, "peer_memory": sh.peer_memory}
         sh.close()
     ctx.close()
     del d_whole, d_ref, d_shard, d_all
