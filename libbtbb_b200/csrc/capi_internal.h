@@ -172,6 +172,7 @@ int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_l
 int bt_decode_one_cpu(const char *symbols, int length, uint32_t clkn, uint8_t uap, int whitened, uint8_t type,
 		      int mode, btbb_b200_decoded *out);
 int bt_header_present_cpu(const char *symbols, int length);
+int bt_try_clock_cpu(const char *symbols, int length, int clock, int whitened, uint8_t *uap, uint8_t *type);
 
 /* capi.cu */
 int bt_find_first_host(btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,

@@ -4,9 +4,12 @@
  *
  * struct btbb_packet keeps the upstream field order and sizes (bluetooth_packet.h:52-112,
  * 5952 bytes) because bluetooth_piconet.c and the pcap writers poke at it directly when
- * they are compiled into the same library.  Accessors are plain host C;
- * everything that is arithmetic on symbols goes to the GPU -- there is no CPU code path
- * for btbb_find_ac / btbb_decode* / try_clock / crc_check here.
+ * they are compiled into the same library.  Accessors are plain host C.
+ * Routing (btbb_b200_classic_config): a classic call carries ONE packet or one short buffer, so by
+ * default single-packet calls and searches of at most 8192 positions are answered by the host
+ * small-call path (decode_host.cpp / find_ac_host.cpp: the kernels' own arithmetic from decode_core.h
+ * and bt_math.h compiled for the host -- never oracle/), longer searches by the kernels; with
+ * BTBB_B200_CLASSIC=gpu every call launches kernels.  The batch entry points never take the host path.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -295,6 +298,15 @@ static void store_payload(btbb_packet *p, const btbb_b200_decoded *r)
 
 uint8_t try_clock(int clock, btbb_packet *p)
 {
+	route_init();
+	if (!g_packet_gpu.load()) {
+		uint8_t uap, type;
+		if (!bt_try_clock_cpu(p->symbols, p->length, clock, btbb_packet_get_flag(p, BTBB_WHITENED), &uap, &type))
+			return 0;             /* unfec13 failed: packet untouched (:1186-1187) */
+		p->UAP = uap;
+		p->packet_type = type;
+		return p->UAP;
+	}
 	static thread_local btbb_b200_decoded rec[64];
 	if (run_chain(p, BTBB_B200_MODE_TRY_CLOCKS, 0, rec)) return 0;
 	const btbb_b200_decoded *r = &rec[clock & 63];

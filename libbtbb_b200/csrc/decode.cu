@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(WARPS * 32, OUT == OUT_FULL64 ? 1 : 3) decode_
 				type_mask = header_ok ? 1u << s.type : 0u;
 			} else {
 				s.uap = in.uap; s.type = in.type & 15;
-				type_mask = 1u << s.type;
+				type_mask = btd_kind_type_mask(mode == BTBB_B200_MODE_PAYLOAD ? BTD_KIND_PAYLOAD
+							       : mode == BTBB_B200_MODE_CRC_CHECK ? BTD_KIND_CRC_CHECK
+							       : BTD_KIND_RAW + (mode - BTBB_B200_MODE_RAW), s.type);
 			}
 		} else {
 			/* packet type under clock candidates lane and lane + 32 (try_clock's type field alone) */

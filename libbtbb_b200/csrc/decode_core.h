@@ -233,6 +233,25 @@ BT_HD void btd_needs_for(uint32_t type_mask, int length, int payload_kind, btd_n
 	n->symbols = sy;
 }
 
+/* The packet types whose state the evaluation of (kind, type) can touch.  crc_check and
+ * btbb_decode_payload dispatch on the type; a single type decoder (BTD_KIND_RAW + n) runs whatever the
+ * packet's type field says -- fhs(), EV3(), EV4(), EV5() ignore it, DM(), DH() and HV() switch on it and
+ * give up on a type that is not theirs (:898-1174). */
+BT_HD uint32_t btd_kind_type_mask(int kind, uint32_t type)
+{
+	const uint32_t own = 1u << (type & 15u);
+	if (kind < BTD_KIND_RAW) return own;
+	switch (kind - BTD_KIND_RAW) {
+	case 0: return 1u << 2;
+	case 1: return own & ((1u << 3) | (1u << 8) | (1u << 10) | (1u << 14));
+	case 2: return own & ((1u << 4) | (1u << 9) | (1u << 11) | (1u << 15));
+	case 3: return 1u << 7;
+	case 4: return 1u << 12;
+	case 5: return 1u << 13;
+	default: return own & ((1u << 5) | (1u << 6) | (1u << 7));
+	}
+}
+
 /* ---- per (packet, clock) evaluation ---- */
 BT_HD void btd_lane_init(btd_lane &s, int clock)
 {

@@ -14,32 +14,75 @@
 #include "scan_hash.h"
 #include "capi_internal.h"
 
-static inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+#include <mutex>
+
+namespace {
+
+inline int popc64(uint64_t v) { return __builtin_popcountll(v); }
+
+/* gen_syndrome (bluetooth_packet.c:147-159) by bytes of the information part: the remainder is linear,
+ * so cw mod g(x) = low 34 bits XOR one table entry per byte of cw >> 34.  Also the Barker verdict of
+ * every 7-bit tail: 0 = further than 1 from both tails, else the tail to put in its place. */
+struct host_tables {
+	uint64_t rem[4][256];
+	uint8_t tail[128];
+};
+const host_tables &tables()
+{
+	static host_tables T;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		for (int j = 0; j < 4; j++)
+			for (int v = 0; v < 256; v++)
+				T.rem[j][v] = bt_syndrome_slow((uint64_t)v << (34 + 8 * j)) & 0x3ffffffffULL;
+		for (int t = 0; t < 128; t++) {
+			const int da = __builtin_popcount((unsigned)t ^ BT_BARKER_A);      /* BARKER_DISTANCE <= 1 (:55-59, :385) */
+			T.tail[t] = da <= 1 ? (uint8_t)BT_BARKER_A : da >= 6 ? (uint8_t)BT_BARKER_B : 0;
+		}
+		static_assert(BT_BARKER_A != 0 && BT_BARKER_B != 0, "0 marks a rejected tail");
+	});
+	return T;
+}
+
+const int CHUNK = 4096;      /* positions per packed block */
+
+}  // namespace
 
 int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,
 		      int max_ac_errors, btbb_b200_hit *hit, int *found)
 {
 	*found = 0;
 	if (search_length <= 0) return BTBB_B200_OK;
+	const host_tables &T = tables();
 	const bool known = lap != BTBB_B200_LAP_ANY;
 	const uint64_t ac = known ? bt_gen_syncword(lap) : 0;
-	uint64_t w = 0;
-	for (int i = 0; i < 64; i++) w |= (uint64_t)(stream[i] & 1) << i;      /* air_to_host64 (:235-242) */
-	for (int p = 0; p < search_length; p++) {
-		if (known) {                                   /* find_known_lap (:430-438) */
-			const int d = popc64(w ^ ac);
-			if (d <= max_ac_errors) {
-				hit->offset = p; hit->lap = lap; hit->ac_errors = (uint8_t)d;
-				hit->pad[0] = hit->pad[1] = hit->pad[2] = 0;
-				*found = 1;
-				return BTBB_B200_OK;
-			}
-		} else {                                       /* promiscuous_packet_search (:385-416) */
-			const uint32_t tail = (uint32_t)(w >> 57);
-			const int da = __builtin_popcount(tail ^ BT_BARKER_A);
-			if (da <= 1 || da >= 6) {                  /* BARKER_DISTANCE <= 1 (:55-59, :385) */
-				uint64_t sw = (w & 0x01ffffffffffffffULL) | ((uint64_t)(da <= 1 ? BT_BARKER_A : BT_BARKER_B) << 57);
-				const uint64_t syn = bt_syndrome_slow(sw ^ BT_PN) & 0x3ffffffffULL;
+	uint64_t bits[CHUNK / 64 + 2];
+	for (int first = 0; first < search_length; first += CHUNK) {
+		/* air_to_host64 (:235-242) of every window of the block: symbol first + i -> bit i */
+		const int npos = search_length - first < CHUNK ? search_length - first : CHUNK, nsym = npos + 63;
+		const char *s = stream + first;
+		memset(bits, 0, sizeof(bits));
+		int i = 0;
+		for (; i + 8 <= nsym; i += 8) {
+			uint64_t x;
+			memcpy(&x, s + i, 8);
+			bits[i >> 6] |= (((x & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56) << (i & 63);
+		}
+		for (; i < nsym; i++) bits[i >> 6] |= (uint64_t)(s[i] & 1) << (i & 63);
+		for (int p = 0; p < npos; p++) {
+			const int sh = p & 63;
+			const uint64_t w = sh ? (bits[p >> 6] >> sh) | (bits[(p >> 6) + 1] << (64 - sh)) : bits[p >> 6];
+			if (known) {                                   /* find_known_lap (:430-438) */
+				const int d = popc64(w ^ ac);
+				if (d > max_ac_errors) continue;
+				hit->offset = first + p; hit->lap = lap; hit->ac_errors = (uint8_t)d;
+			} else {                                       /* promiscuous_packet_search (:385-416) */
+				const uint64_t tail = T.tail[w >> 57];
+				if (!tail) continue;
+				uint64_t sw = (w & 0x01ffffffffffffffULL) | (tail << 57);
+				const uint64_t c = sw ^ BT_PN, info = c >> 34;
+				const uint64_t syn = (c & 0x3ffffffffULL) ^ T.rem[0][info & 255] ^ T.rem[1][(info >> 8) & 255] ^
+						     T.rem[2][(info >> 16) & 255] ^ T.rem[3][info >> 24];
 				int e = 0;
 				if (syn) {
 					e = 0xff;
@@ -54,15 +97,13 @@ int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_l
 						}
 					}
 				}
-				if (e <= max_ac_errors) {
-					hit->offset = p; hit->lap = (uint32_t)(sw >> 34) & 0xffffffu; hit->ac_errors = (uint8_t)e;
-					hit->pad[0] = hit->pad[1] = hit->pad[2] = 0;
-					*found = 1;
-					return BTBB_B200_OK;
-				}
+				if (e > max_ac_errors) continue;
+				hit->offset = first + p; hit->lap = (uint32_t)(sw >> 34) & 0xffffffu; hit->ac_errors = (uint8_t)e;
 			}
+			hit->pad[0] = hit->pad[1] = hit->pad[2] = 0;
+			*found = 1;
+			return BTBB_B200_OK;
 		}
-		if (p + 1 < search_length) w = (w >> 1) | ((uint64_t)(stream[p + 64] & 1) << 63);
 	}
 	return BTBB_B200_OK;
 }

@@ -685,6 +685,35 @@ void orc_try_clock_one(const char *symbols, int length, int clock, int whitened,
 	emit(&p, ok, rv, out);
 }
 
+/* One decoder on a packet whose UAP and type field the caller forces -- what the exported per-type
+ * functions (bluetooth_packet.h:115-144) do when they are called directly: fn 0 fhs, 1 DM, 2 DH, 3 EV3,
+ * 4 EV4, 5 EV5, 6 HV; -1 btbb_decode_payload, -2 crc_check.  header_ok = the header's unfec13 verdict;
+ * raw != 0: payload bytes as the decoder left them, whatever rv says.  Not thread-safe with raw. */
+void orc_typed_one(const char *symbols, int length, int clock, uint8_t uap, uint8_t type, int whitened,
+		   int fn, int raw, btbb_b200_decoded *out)
+{
+	static __thread opkt p;
+	char h[18];
+	int ok, rv;
+	opkt_load(&p, symbols, length, whitened);
+	p.uap = uap; p.type = type;
+	ok = orc_unfec13(p.sym + 68, h, 18);
+	switch (fn) {
+	case -2: rv = do_crc_check(&p, clock); break;
+	case -1: rv = do_decode_payload(&p, clock); break;
+	case 0: rv = dec_fhs(&p, clock); break;
+	case 1: rv = dec_dm(&p, clock); break;
+	case 2: rv = dec_dh(&p, clock); break;
+	case 3: rv = dec_ev35(&p, clock, 32); break;
+	case 4: rv = dec_ev4(&p, clock); break;
+	case 5: rv = dec_ev35(&p, clock, 182); break;
+	default: rv = dec_hv(&p, clock); break;
+	}
+	g_emit_raw = raw;
+	emit(&p, ok, rv, out);
+	g_emit_raw = 0;
+}
+
 /* btbb_header_present (:1371-1408) */
 int orc_header_present(const char *s, int length)
 {

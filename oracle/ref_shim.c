@@ -236,6 +236,39 @@ void ref_decode_one_raw(char *symbols, int length, uint32_t clkn, uint8_t uap, i
 	btbb_packet_unref(p);
 }
 
+/* one of the exported per-type decoders (bluetooth_packet.h:115-144: fn 0 fhs, 1 DM, 2 DH, 3 EV3, 4 EV4,
+ * 5 EV5, 6 HV), btbb_decode_payload (-1) or crc_check (-2) on a packet whose UAP and type the caller forces */
+void ref_typed_one(char *symbols, int length, int clock, uint8_t uap, uint8_t type, int whitened, int fn, int raw,
+		   ref_decoded *out)
+{
+	btbb_packet *p = btbb_packet_new();
+	char h[18];
+	int i;
+	memset(out, 0, sizeof(*out));
+	p->flags = 0;
+	btbb_packet_set_flag(p, BTBB_WHITENED, whitened);
+	btbb_packet_set_data(p, symbols, length, 0, (uint32_t)clock << 1);
+	btbb_packet_set_uap(p, uap);
+	p->packet_type = type;
+	out->header_ok = unfec13(p->symbols + 68, h, 18);
+	switch (fn) {
+	case -2: out->rv = crc_check(clock, p); break;
+	case -1: out->rv = btbb_decode_payload(p); break;
+	case 0: out->rv = fhs(clock, p); break;
+	case 1: out->rv = DM(clock, p); break;
+	case 2: out->rv = DH(clock, p); break;
+	case 3: out->rv = EV3(clock, p); break;
+	case 4: out->rv = EV4(clock, p); break;
+	case 5: out->rv = EV5(clock, p); break;
+	default: out->rv = HV(clock, p); break;
+	}
+	fill_decoded(p, out);
+	if (raw && p->payload_length > 0 && p->payload_length <= 344)
+		for (i = 0; i < p->payload_length; i++)
+			out->payload[i] = air_to_host8(&p->payload[i * 8], 8);
+	btbb_packet_unref(p);
+}
+
 /* try_clock + crc_check for one clock candidate (SURVEY 3.4 inner loop) */
 void ref_try_clock_one(char *symbols, int length, int clock, int whitened, ref_decoded *out)
 {

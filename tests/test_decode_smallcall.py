@@ -112,3 +112,71 @@ def test_crafted_crc_success_paths(orc):
         seen["ev35"] += int(want["rv"] == 10)
     assert seen["ev4"] > 25 and seen["fhs_own"] > 20 and seen["fhs_other"] > 20 and seen["dv"] > 40, seen
     assert seen["ev35"] >= 3 and seen["ev4_fecfail"] > 5, seen
+
+
+def test_host_packet_state_is_reused_without_changing_any_answer(orc):
+    """The host path keeps the clock-independent state of the last packet and grows it on demand
+    (decode_host.cpp).  Whatever the order of the questions -- short decoders first, then long ones,
+    crc_check after a raw decoder, the 64-clock sweep in between -- every answer equals the one a
+    fresh state gives (another packet in between evicts the entry)."""
+    rng = np.random.default_rng(31337)
+    other = rng.integers(0, 2, 3125, dtype=np.uint8)
+    modes = [B.MODE_DECODE, B.MODE_PAYLOAD, B.MODE_CRC_CHECK] + [B.MODE_RAW + k for k in range(7)]
+    for i in range(60):
+        sym = rng.integers(0, 2, 3125, dtype=np.uint8)
+        sym[68:122] = np.repeat(rng.integers(0, 2, 18, dtype=np.uint8), 3)
+        if i % 2 == 0:
+            for b, d in enumerate(rng.integers(0, 1024, 183)):
+                cw = orc.orc_fec23(int(d))
+                sym[122 + 15 * b:122 + 15 * b + 15] = [(cw >> t) & 1 for t in range(15)]
+            if i % 4 == 0:      # one uncorrectable block somewhere: fail indices must survive growing
+                b = int(rng.integers(0, 60))
+                sym[122 + 15 * b:122 + 15 * b + 15] ^= 1
+                sym[122 + 15 * b + 3] ^= 1
+        n = int(rng.choice([3125, 3125, 1500, 700, 362, 250]))
+        calls = []
+        for _ in range(40):
+            m = int(rng.choice(modes)) | (B.MODE_FLAG_RAW_PAYLOAD if rng.integers(0, 2) else 0)
+            calls.append((m, int(rng.integers(0, 64)), int(rng.integers(0, 256)), int(rng.integers(0, 16)), int(rng.integers(0, 2))))
+        fresh = []
+        for m, clk, uap, t, w in calls:
+            B.decode_smallcall(other, 3125, 0, 0)                       # evict
+            fresh.append(B.decode_smallcall(sym, n, clk, uap, whitened=w, ptype=t, mode=m)[0].tobytes())
+        B.decode_smallcall(other, 3125, 0, 0)
+        sweep_fresh = B.decode_smallcall(sym, n, mode=B.MODE_TRY_CLOCKS).tobytes()
+        B.decode_smallcall(other, 3125, 0, 0)
+        order = rng.permutation(len(calls))
+        for j, k in enumerate(order):
+            m, clk, uap, t, w = calls[k]
+            assert B.decode_smallcall(sym, n, clk, uap, whitened=w, ptype=t, mode=m)[0].tobytes() == fresh[k], (i, k, calls[k])
+            if j == 20:
+                assert B.decode_smallcall(sym, n, mode=B.MODE_TRY_CLOCKS).tobytes() == sweep_fresh, i
+        # a rewritten packet at the same address is a different packet
+        sym2 = sym.copy()
+        sym2[130:400] ^= rng.integers(0, 2, 270, dtype=np.uint8)
+        m, clk, uap, t, w = calls[0]
+        a = B.decode_smallcall(sym2, n, clk, uap, whitened=w, ptype=t, mode=m)[0].tobytes()
+        sym[:] = sym2
+        assert B.decode_smallcall(sym, n, clk, uap, whitened=w, ptype=t, mode=m)[0].tobytes() == a
+
+
+def test_single_decoders_with_a_forced_type(orc):
+    """fhs() / DM() / DH() / EV3() / EV4() / EV5() / HV(), btbb_decode_payload and crc_check called
+    directly on a packet whose type field was set by the caller (bluetooth_packet.h:115-144) -- also a
+    type that is not the decoder's own: oracle against the unmodified reference where it was built,
+    host path against the oracle."""
+    rng = np.random.default_rng(60606)
+    R = util.ref() if util.have_ref() else None
+    if R is not None:
+        R.btbb_init(2)
+    seen = set()
+    for i, (sym, n, clk, uap, t, fn, w) in enumerate(util.forced_type_cases(orc, rng, 1500)):
+        for raw in (0, 1):
+            want = util.typed_one(orc, "orc", sym, n, clk, uap, t, fn, w, raw)
+            if R is not None:
+                _cmp(want, util.typed_one(R, "ref", sym, n, clk, uap, t, fn, w, raw), (i, "oracle vs reference", fn, t, n, raw))
+            got = B.decode_smallcall(sym, n, clk, uap, whitened=w, ptype=t,
+                                     mode=util.mode_of_fn(fn) | (B.MODE_FLAG_RAW_PAYLOAD if raw else 0))[0]
+            _cmp(got, want, (i, "host vs oracle", fn, t, n, raw))
+        seen.add((fn, int(want["rv"])))
+    assert len(seen) >= 18, sorted(seen)

@@ -174,3 +174,29 @@ def test_device_entry_points_match_smallcall_and_compact(gpu_ctx2, product_lib):
     tc = d_tc.cpu().numpy().view(np.uint16).reshape(len(pl), 64)
     cls = np.select([ref1["rv"] == 0, ref1["rv"] == 1, ref1["rv"] == 2, ref1["rv"] == 10], [0, 1, 2, 3], 4)
     assert ((tc & 0xff) == ref1["uap"]).all() and ((tc >> 8) == cls).all()
+
+
+def test_single_decoders_with_a_forced_type_on_gpu(gpu_ctx2, orc):
+    """BTBB_B200_MODE_PAYLOAD / _CRC_CHECK / _RAW + n with a caller-forced type field (matching the
+    decoder or not), plain and with the raw-payload flag: every record against the oracle (which
+    tests/test_decode_smallcall.py pins to the reference's exported fhs() / DM() / ... for these calls)."""
+    rng = np.random.default_rng(60606)
+    cases = list(util.forced_type_cases(orc, rng, 1800))
+    s = np.concatenate([c[0] for c in cases])
+    by_fn = {}
+    for i, c in enumerate(cases):
+        by_fn.setdefault(c[5], []).append(i)
+    checked = 0
+    for fn, idx in sorted(by_fn.items()):
+        pk = np.zeros(len(idx), dtype=B.PKTIN_DTYPE)
+        for j, i in enumerate(idx):
+            _, n, clk, uap, t, _, w = cases[i]
+            pk[j]["offset"], pk[j]["length"], pk[j]["clkn"], pk[j]["uap"], pk[j]["whitened"], pk[j]["type"] = i * 3125, n, clk, uap, w, t
+        for raw in (0, 1):
+            got = gpu_ctx2.decode_host(s, pk, mode=util.mode_of_fn(fn) | (B.MODE_FLAG_RAW_PAYLOAD if raw else 0))
+            for j, i in enumerate(idx):
+                sym, n, clk, uap, t, _, w = cases[i]
+                want = util.typed_one(orc, "orc", sym, n, clk, uap, t, fn, w, raw)
+                assert got[j].tobytes() == want.tobytes(), (fn, i, t, n, raw, got[j], want)
+                checked += 1
+    assert checked == 2 * len(cases) and len(by_fn) == 9

@@ -48,6 +48,8 @@ def oracle():
         L.orc_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_decode_one_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.orc_header_present.argtypes = [C.c_void_p, C.c_int]
+        L.orc_typed_one.restype = None
+        L.orc_typed_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint8, C.c_uint8, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_hop_sequence.restype = None
         L.orc_hop_sequence.argtypes = [C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_uap_sieve.restype = None
@@ -85,6 +87,8 @@ def ref():
         L.ref_try_clock_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_decode_one_raw.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint8, C.c_int, C.c_void_p]
         L.ref_header_present.argtypes = [C.c_void_p, C.c_int]
+        L.ref_typed_one.restype = None
+        L.ref_typed_one.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint8, C.c_uint8, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_hop_sequence.restype = None
         L.ref_hop_sequence.argtypes = [C.c_uint32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         L.ref_uap_sieve.restype = None
@@ -112,6 +116,40 @@ def decode_one_raw(L, prefix, stream, off, length, clk, uap, whitened=1):
     d = np.zeros(1, dtype=B.DECODED_DTYPE)
     getattr(L, prefix + "_decode_one_raw")(stream[off:].ctypes.data, length, clk, uap, whitened, d.ctypes.data)
     return d[0]
+
+
+def typed_one(L, prefix, sym, length, clock, uap, ptype, fn, whitened=1, raw=0):
+    """One forced-type decoder call: fn 0 fhs, 1 DM, 2 DH, 3 EV3, 4 EV4, 5 EV5, 6 HV, -1 btbb_decode_payload, -2 crc_check."""
+    d = np.zeros(1, dtype=B.DECODED_DTYPE)
+    getattr(L, prefix + "_typed_one")(sym.ctypes.data, length, clock, uap, ptype, whitened, fn, raw, d.ctypes.data)
+    return d[0]
+
+
+def mode_of_fn(fn):
+    return B.MODE_CRC_CHECK if fn == -2 else B.MODE_PAYLOAD if fn == -1 else B.MODE_RAW + fn
+
+
+def forced_type_cases(orc, rng, n):
+    """(sym, length, clock, uap, type, fn, whitened): noise and FEC-clean packets for the single decoders,
+    the type field forced -- matching the decoder or not."""
+    own = {0: [2], 1: [3, 8, 10, 14], 2: [4, 9, 11, 15], 3: [7], 4: [12], 5: [13], 6: [5, 6, 7]}
+    for i in range(n):
+        sym = rng.integers(0, 2, 3125, dtype=np.uint8)
+        sym[68:122] = np.repeat(rng.integers(0, 2, 18, dtype=np.uint8), 3)
+        if i % 5 == 4:
+            sym[68 + 3 * int(rng.integers(0, 18))] ^= 1
+        if i % 2 == 0:
+            for b, d in enumerate(rng.integers(0, 1024, 183)):
+                cw = orc.orc_fec23(int(d))
+                sym[122 + 15 * b:122 + 15 * b + 15] = [(cw >> t) & 1 for t in range(15)]
+            if i % 6 == 0:
+                b = int(rng.integers(0, 40))
+                sym[122 + 15 * b:122 + 15 * b + 15] ^= 1
+                sym[122 + 15 * b + 3] ^= 1
+        length = int(rng.choice([3125, 3125, 1500, 700, 362, 361, 250, 140, 122, 100]))
+        fn = int(rng.integers(-2, 7))
+        ptype = int(rng.choice(own[fn])) if fn >= 0 and rng.integers(0, 3) else int(rng.integers(0, 16))
+        yield sym, length, int(rng.integers(0, 64)), int(rng.integers(0, 256)), ptype, fn, int(rng.integers(0, 8) != 0)
 
 
 def try_clock_one(L, prefix, stream, off, length, clock, whitened=1):
