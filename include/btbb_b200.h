@@ -383,6 +383,17 @@ int64_t btbb_b200_pcapng_bredr_blocks(const btbb_b200_hit *hits, const btbb_b200
 				      const btbb_b200_pcap_meta *meta, int64_t n,
 				      uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap);
 
+/* The two formatters above on the device (pcap_dev.cu): hits, dec, meta and out are DEVICE pointers, so
+ * the batch chain's records are serialised where they lie and only the file bytes (38 + payload bytes per
+ * packet instead of a 16-byte hit + 372-byte record) cross PCIe.  format 0 = pcap records, 1 = pcapng
+ * enhanced packet blocks; byte-identical to the host formatters.  *bytes (host) receives the size of the
+ * n records; they are written only when that fits in cap (d_out may be NULL to ask for the size).
+ * Synchronises the stream. */
+int btbb_b200_capture_records_dev(btbb_b200_ctx *ctx, int format, const btbb_b200_hit *d_hits,
+				  const btbb_b200_decoded *d_dec, const btbb_b200_pcap_meta *d_meta, int64_t n,
+				  uint32_t reflap, uint8_t refuap, uint8_t *d_out, int64_t cap, int64_t *bytes,
+				  void *cuda_stream);
+
 /* ---- synthetic capture generator (SURVEY.md 8d "Synthetic input"; test/bench data only) ---- */
 typedef struct btbb_b200_synth_cfg {
 	uint64_t seed;          /* 0xB200B7BB by default */

@@ -20,7 +20,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libbtbb.so.1")
 STATIC = os.path.join(LIBDIR, "libbtbb.a")
 SOURCES = ["capi.cu", "tables.cu", "find_ac.cu", "decode.cu", "decode_tables.cpp", "decode_host.cpp", "find_ac_host.cpp", "sieve.cu",
-           "hops.cu", "synth.cu", "compat.cu", "host_pack.cpp", "pcap_out.cpp", "sharded.cu"]
+           "hops.cu", "synth.cu", "compat.cu", "host_pack.cpp", "pcap_out.cpp", "pcap_dev.cu", "sharded.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC,-fvisibility=default"]
@@ -75,7 +75,29 @@ def build(force=False, verbose=False, ptxas_verbose=False):
         if os.path.exists(STATIC):
             os.remove(STATIC)
         subprocess.run(["ar", "rcs", STATIC] + objs, check=False)
+    _dev_files()
     return LIB
+
+
+def _dev_files():
+    """What upstream's install step adds for callers that build against the library: the unversioned
+    libbtbb.so link (lib/src/CMakeLists.txt:43-52) and libbtbb.pc (lib/libbtbb.pc.in:6-10), here with
+    this tree as the prefix -- `PKG_CONFIG_PATH=libbtbb_b200/lib/pkgconfig pkg-config --cflags --libs libbtbb`."""
+    link = os.path.join(LIBDIR, "libbtbb.so")
+    if not os.path.islink(link):
+        if os.path.exists(link):
+            os.remove(link)
+        os.symlink("libbtbb.so.1", link)
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")
+    pc = ("prefix=%s\nlibdir=%s\nincludedir=${prefix}/include\n\n"
+          "Name: Bluetooth Baseband Library\nDescription: C Utility Library (B200 build of the packet layer)\n"
+          "Version: 0.1-b200\nCflags: -I${includedir}/\nLibs: -L${libdir} -lbtbb\n"
+          "Libs.private: -L%s -lcudart -lstdc++ -lm -ldl -lpthread\n") % (os.path.abspath(os.path.join(HERE, "..")), LIBDIR, cuda_lib)
+    os.makedirs(os.path.join(LIBDIR, "pkgconfig"), exist_ok=True)
+    path = os.path.join(LIBDIR, "pkgconfig", "libbtbb.pc")
+    if not os.path.exists(path) or open(path).read() != pc:
+        with open(path, "w") as f:
+            f.write(pc)
 
 
 FULL_LIB = os.path.join(LIBDIR, "full", "libbtbb.so.1")

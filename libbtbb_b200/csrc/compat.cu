@@ -128,7 +128,7 @@ int btbb_init(int max_ac_errors)
 }
 
 #ifndef BTBB_B200_RELEASE
-#define BTBB_B200_RELEASE "b200-r1"
+#define BTBB_B200_RELEASE "b200-r2"
 #endif
 const char *btbb_get_release(void) { return BTBB_B200_RELEASE; }
 const char *btbb_get_version(void) { return "libbtbb-b200 0.1 (sm_100a)"; }

@@ -124,3 +124,36 @@ def test_group_by_lap_is_a_stable_grouping(product_lib):
         for g, lap in enumerate(laps):
             grp = hits[order[gs[g]:gs[g + 1]]]
             assert (grp["lap"] == lap).all() and (np.diff(grp["offset"]) >= 0).all()
+
+
+def test_pkg_config_and_static_library(product_lib, tmp_path):
+    """The rest of upstream's build contract (lib/libbtbb.pc.in:6-10, lib/src/CMakeLists.txt:43-63): a
+    caller that asks pkg-config for its flags links against the unversioned libbtbb.so, and the same
+    caller links statically against libbtbb.a with the private libraries the .pc file names."""
+    import shutil
+    import subprocess
+    import torch
+    from libbtbb_b200 import build
+    if not shutil.which("pkg-config"):
+        pytest.skip("no pkg-config here")
+    build._dev_files()
+    env = dict(os.environ, PKG_CONFIG_PATH=os.path.join(os.path.dirname(B.LIB_PATH), "pkgconfig"))
+    pc = lambda *a: subprocess.run(["pkg-config", *a, "libbtbb"], env=env, capture_output=True, text=True, check=True).stdout.split()
+    assert "-lbtbb" in pc("--libs")
+    src = tmp_path / "caller.c"
+    src.write_text(C_CALLER)
+    libdir = os.path.dirname(B.LIB_PATH)
+    want_rc = 0 if torch.cuda.is_available() else -2
+    dyn = tmp_path / "caller_dyn"
+    subprocess.run(["gcc", "-std=c99", str(src), *pc("--cflags", "--libs"), f"-Wl,-rpath,{libdir}", "-o", str(dyn)], check=True)
+    out = subprocess.run([str(dyn)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == want_rc and out[3] == "4e7a2cce331a3ae2"
+    assert os.path.exists(build.STATIC)
+    private = [f for f in pc("--static", "--libs") if f != "-lbtbb"]
+    rpaths = [f"-Wl,-rpath,{f[2:]}" for f in private if f.startswith("-L")]
+    sta = tmp_path / "caller_static"
+    subprocess.run(["gcc", "-std=c99", str(src), *pc("--cflags"), build.STATIC, *private, *rpaths, "-o", str(sta)], check=True)
+    out = subprocess.run([str(sta)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == want_rc and out[3] == "4e7a2cce331a3ae2"
+    ldd = subprocess.run(["ldd", str(sta)], capture_output=True, text=True).stdout
+    assert "libbtbb" not in ldd

@@ -110,3 +110,77 @@ def test_gpu_records_to_pcap_files(gpu_ctx2, orc, product_lib, tmp_path):
     assert [len(png), hashlib.sha256(png).hexdigest()] == g["pcapng_blocks"]
     if util.have_ref():
         assert pcap == test_pcap._ref_pcap(tmp_path, s, hits, dec, meta)
+
+
+def test_capture_records_formatted_on_the_device(gpu_ctx2, product_lib):
+    """btbb_b200_capture_records_dev == the host formatters, byte for byte: GPU hit and decode records of
+    the 79-channel capture (failed decodes included), then records with every payload length 0..400+ and
+    odd metadata so that each padding / flag case of both formats occurs; size query, short buffer, n = 0."""
+    import ctypes as C
+    import torch
+    g = json.load(open(os.path.join(util.GOLDEN, "chain79.json")))
+    cfg, s, n = util.chain79_case(g["blocks"])
+    d = torch.from_numpy(s).cuda()
+    cap = 4096
+    d_hits = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    cnt, rc = gpu_ctx2.find_ac_dev(d.data_ptr(), n, d_hits.data_ptr(), cap, lap=B.LAP_ANY, k=2)
+    hits = d_hits[:cnt].cpu().numpy().reshape(-1).view(B.HIT_DTYPE)
+    dec, sv, gs, laps = util.chain79_packets(cfg, hits)
+    d_pk = torch.from_numpy(dec.view(np.uint8)).cuda()
+    d_rec = torch.zeros((cnt, 372), dtype=torch.uint8, device="cuda")
+    B.check(product_lib.btbb_b200_decode_dev(gpu_ctx2.h, d.data_ptr(), n + 63, d_pk.data_ptr(), cnt,
+                                             B.MODE_DECODE | B.MODE_FLAG_RAW_PAYLOAD, d_rec.data_ptr(), 0))
+    torch.cuda.synchronize()
+    recs = d_rec.cpu().numpy().reshape(-1).view(B.DECODED_DTYPE)
+    meta = util.chain79_meta(dec)
+
+    def on_device(hits_h, recs_h, meta_h, fmt, reflap=B.LAP_ANY, refuap=0xFF, short=False):
+        dh = torch.from_numpy(np.ascontiguousarray(hits_h).view(np.uint8).copy()).cuda()
+        dr = torch.from_numpy(np.ascontiguousarray(recs_h).view(np.uint8).copy()).cuda()
+        dm = torch.from_numpy(np.ascontiguousarray(meta_h).view(np.uint8).copy()).cuda()
+        need = C.c_int64(-1)
+        B.check(product_lib.btbb_b200_capture_records_dev(gpu_ctx2.h, fmt, dh.data_ptr(), dr.data_ptr(), dm.data_ptr(), len(hits_h),
+                                                          reflap, refuap, None, 0, C.byref(need), None))
+        out = torch.full((max(need.value, 1) + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+        got = C.c_int64(-1)
+        give = need.value - 1 if short else need.value
+        B.check(product_lib.btbb_b200_capture_records_dev(gpu_ctx2.h, fmt, dh.data_ptr(), dr.data_ptr(), dm.data_ptr(), len(hits_h),
+                                                          reflap, refuap, out.data_ptr(), give, C.byref(got), None))
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        assert got.value == need.value
+        if short:
+            assert (o == 0xAB).all()                       # nothing written when it does not fit
+            return None
+        assert (o[need.value:] == 0xAB).all()              # nothing written past the end
+        return o[:need.value].tobytes()
+
+    assert on_device(hits, recs, meta, 0) == B.pcap_bredr(hits, recs, meta)
+    assert on_device(hits, recs, meta, 1) == B.pcapng_bredr_blocks(hits, recs, meta)
+    # synthetic records: every payload length, both sides of every branch of the flag word
+    rng = np.random.default_rng(12)
+    m = 3000
+    h2 = np.zeros(m, dtype=B.HIT_DTYPE)
+    h2["offset"] = np.arange(m) * 4000
+    h2["lap"] = rng.integers(0, 1 << 24, m)
+    h2["ac_errors"] = rng.integers(0, 6, m)
+    r2 = np.zeros(m, dtype=B.DECODED_DTYPE)
+    r2["payload_length"] = np.concatenate([np.arange(0, 420), rng.integers(-3, 420, m - 420)])
+    r2["payload"] = rng.integers(0, 256, (m, 344), dtype=np.uint8)
+    r2["header_packed"] = rng.integers(0, 1 << 18, m)
+    m2 = np.zeros(m, dtype=B.PCAP_META_DTYPE)
+    m2["ns"] = rng.integers(0, 1 << 62, m, dtype=np.uint64)
+    m2["sigdbm"] = rng.integers(-100, 10, m)
+    m2["noisedbm"] = rng.integers(-100, 10, m)
+    m2["channel"] = rng.integers(0, 79, m)
+    m2["transport"] = rng.integers(0, 4, m)
+    m2["modulation"] = rng.integers(0, 3, m)
+    for reflap, refuap in ((B.LAP_ANY, 0xFF), (0x9E8B33, 0x47), (0x123456, 0xFF)):
+        assert on_device(h2, r2, m2, 0, reflap, refuap) == B.pcap_bredr(h2, r2, m2, reflap, refuap)
+        assert on_device(h2, r2, m2, 1, reflap, refuap) == B.pcapng_bredr_blocks(h2, r2, m2, reflap, refuap)
+    for k in (1, 7, 1023, 1024, 1025, 2049):
+        assert on_device(h2[:k], r2[:k], m2[:k], 1) == B.pcapng_bredr_blocks(h2[:k], r2[:k], m2[:k])
+    assert on_device(h2, r2, m2, 0, short=True) is None
+    z = C.c_int64(-1)
+    B.check(product_lib.btbb_b200_capture_records_dev(gpu_ctx2.h, 0, None, None, None, 0, B.LAP_ANY, 0xFF, None, 0, C.byref(z), None))
+    assert z.value == 0

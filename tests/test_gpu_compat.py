@@ -83,3 +83,86 @@ def test_classic_find_ac_and_decode(product_lib, orc, route):
     assert off == (int(w[0]["offset"]) if len(w) else -1)
     L.btbb_packet_unref(pkt)
     L.btbb_b200_classic_config(8192, 0)
+
+
+C_COMPUTE_CALLER = r"""
+/* an existing libbtbb caller, plain C99, linked with -lbtbb: the batch C ABI and the classic calls
+ * doing real work on the GPU -- prints what it found for the test to compare with the oracle */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "btbb.h"
+#include "btbb_b200.h"
+
+int main(void)
+{
+	btbb_b200_ctx *ctx = NULL;
+	btbb_b200_synth_cfg cfg;
+	btbb_b200_hit *hits;
+	btbb_packet *pkt = NULL;
+	int64_t n = 3000000, cap = 4096, got = 0, i;
+	unsigned long long sum = 0;
+	uint8_t *s;
+	int off, rv;
+	if (btbb_b200_create(0, 2, &ctx) != BTBB_B200_OK) { fprintf(stderr, "%s\n", btbb_b200_last_error()); return 1; }
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.seed = 4711; cfg.n_symbols = n + 63; cfg.stride = 5000; cfg.n_laps = 64;
+	cfg.ber_q32 = 4294967;      /* 0.1 % */
+	cfg.packet_mix = (1u << BTBB_B200_KIND_DM1) | (1u << BTBB_B200_KIND_FHS) | (1u << BTBB_B200_KIND_DH1);
+	cfg.fixed_lap = 0x9e8b33;
+	s = malloc((size_t)n + 63);
+	hits = malloc((size_t)cap * sizeof(*hits));
+	if (!s || !hits || btbb_b200_synth_host(&cfg, s) != BTBB_B200_OK) return 2;
+	if (btbb_b200_find_ac_host(ctx, (const char *)s, n, BTBB_B200_LAP_ANY, 2, hits, cap, &got) != BTBB_B200_OK) return 3;
+	for (i = 0; i < got; i++)
+		sum = sum * 1000003ull + (unsigned long long)hits[i].offset * 31ull + hits[i].lap * 7ull + hits[i].ac_errors;
+	printf("%lld %llu\n", (long long)got, sum);
+	/* the classic surface: a search long enough for the kernels, then the per-packet calls */
+	if (btbb_init(2) != 0) return 4;
+	off = btbb_find_ac((char *)s, 100000, LAP_ANY, 2, &pkt);
+	printf("%d %06x %d\n", off, pkt ? btbb_packet_get_lap(pkt) : 0u, pkt ? btbb_packet_get_ac_errors(pkt) : -1);
+	if (off >= 0) {
+		btbb_b200_planted pl;
+		btbb_b200_synth_planted(&cfg, off / cfg.stride, &pl);
+		btbb_packet_set_data(pkt, (char *)s + off, 3125, 0, (uint32_t)pl.clk6 << 1);
+		btbb_packet_set_uap(pkt, pl.uap);
+		btbb_packet_set_flag(pkt, BTBB_CLK6_VALID, 1);
+		rv = btbb_decode_header(pkt) ? btbb_decode_payload(pkt) : -1;
+		printf("%d %d %d\n", rv, btbb_packet_get_type(pkt), btbb_packet_get_payload_length(pkt));
+		btbb_packet_unref(pkt);
+	}
+	btbb_b200_destroy(ctx);
+	free(s); free(hits);
+	return 0;
+}
+"""
+
+
+def test_c99_program_computes_through_the_library(product_lib, orc, tmp_path):
+    """tests/test_abi.py builds a C caller that only creates a context; this one scans, searches and
+    decodes: a C99 program linked against libbtbb.so.1 by SONAME, its output against the oracle."""
+    import os
+    import subprocess
+    src = tmp_path / "compute.c"
+    src.write_text(C_COMPUTE_CALLER)
+    exe = tmp_path / "compute"
+    libdir = os.path.dirname(B.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(util.ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:libbtbb.so.1", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = [l.split() for l in r.stdout.strip().splitlines() if not l.startswith("Packet decoded") and not l.startswith("  ")]
+    n = 3000000
+    cfg = B.synth_cfg(n + 63, stride=5000, ber=4294967 / 2 ** 32, seed=4711, mix=("DM1", "FHS", "DH1"))
+    s = B.synth_host(cfg)
+    orc.orc_init(2)
+    want = util.find_all(orc, "orc", s, n, B.LAP_ANY, 2)
+    acc = 0
+    for h in want:
+        acc = (acc * 1000003 + int(h["offset"]) * 31 + int(h["lap"]) * 7 + int(h["ac_errors"])) % (1 << 64)
+    assert int(lines[0][0]) == len(want) > 500 and int(lines[0][1]) == acc
+    first = want[0]
+    assert int(lines[1][0]) == int(first["offset"]) and int(lines[1][1], 16) == int(first["lap"]) and int(lines[1][2]) == int(first["ac_errors"])
+    p = B.planted(cfg, int(first["offset"]) // 5000)
+    d = util.decode_one(orc, "orc", s, int(first["offset"]), 3125, p.clk6, p.uap)
+    assert [int(x) for x in lines[2]] == [int(d["rv"]) if d["header_ok"] else -1, int(d["type"]), int(d["payload_length"])]
