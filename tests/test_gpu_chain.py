@@ -155,7 +155,7 @@ def test_capture_records_formatted_on_the_device(gpu_ctx2, product_lib):
         assert (o[need.value:] == 0xAB).all()              # nothing written past the end
         return o[:need.value].tobytes()
 
-    assert on_device(hits, recs, meta, 0) == B.pcap_bredr(hits, recs, meta)
+    assert on_device(hits, recs, meta, 0) == B.pcap_bredr(hits, recs, meta)[24:]      # pcap_bredr = file header + records
     assert on_device(hits, recs, meta, 1) == B.pcapng_bredr_blocks(hits, recs, meta)
     # synthetic records: every payload length, both sides of every branch of the flag word
     rng = np.random.default_rng(12)
@@ -176,7 +176,7 @@ def test_capture_records_formatted_on_the_device(gpu_ctx2, product_lib):
     m2["transport"] = rng.integers(0, 4, m)
     m2["modulation"] = rng.integers(0, 3, m)
     for reflap, refuap in ((B.LAP_ANY, 0xFF), (0x9E8B33, 0x47), (0x123456, 0xFF)):
-        assert on_device(h2, r2, m2, 0, reflap, refuap) == B.pcap_bredr(h2, r2, m2, reflap, refuap)
+        assert on_device(h2, r2, m2, 0, reflap, refuap) == B.pcap_bredr(h2, r2, m2, reflap, refuap)[24:]
         assert on_device(h2, r2, m2, 1, reflap, refuap) == B.pcapng_bredr_blocks(h2, r2, m2, reflap, refuap)
     for k in (1, 7, 1023, 1024, 1025, 2049):
         assert on_device(h2[:k], r2[:k], m2[:k], 1) == B.pcapng_bredr_blocks(h2[:k], r2[:k], m2[:k])
