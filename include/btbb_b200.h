@@ -383,6 +383,14 @@ int64_t btbb_b200_pcapng_bredr_blocks(const btbb_b200_hit *hits, const btbb_b200
 				      const btbb_b200_pcap_meta *meta, int64_t n,
 				      uint32_t reflap, uint8_t refuap, uint8_t *out, int64_t cap);
 
+/* ---- host small-call helpers (no device needed) ---- */
+/* The short-search path of the classic btbb_find_ac (searches of at most 8192 positions are answered on
+ * the host, see btbb_b200_classic_config) as a call of its own: FIRST hit of the search the reference
+ * runs after btbb_init(table_errors) -- known LAP or BTBB_B200_LAP_ANY -- *found = 0 if there is none.
+ * table_errors 0..4. */
+int btbb_b200_find_first_smallcall(const char *stream, int search_length, uint32_t lap, int table_errors,
+				   int max_ac_errors, btbb_b200_hit *hit, int *found);
+
 /* The two formatters above on the device (pcap_dev.cu): hits, dec, meta and out are DEVICE pointers, so
  * the batch chain's records are serialised where they lie and only the file bytes (38 + payload bytes per
  * packet instead of a 16-byte hit + 372-byte record) cross PCIe.  format 0 = pcap records, 1 = pcapng

@@ -107,6 +107,7 @@ _PROTOS = {
     "btbb_b200_pcap_file_header": (_i64, [_vp, _i64]),
     "btbb_b200_pcap_bredr_records": (_i64, [_vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64]),
     "btbb_b200_pcapng_bredr_blocks": (_i64, [_vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64]),
+    "btbb_b200_find_first_smallcall": (_int, [_vp, _int, _u32, _int, _int, _vp, C.POINTER(_int)]),
     "btbb_b200_capture_records_dev": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _u32, C.c_uint8, _vp, _i64, C.POINTER(_i64), _vp]),
     "btbb_b200_synth_host": (_int, [C.POINTER(SynthCfg), _vp]),
     "btbb_b200_synth_dev": (_int, [C.POINTER(SynthCfg), _vp, _vp]),

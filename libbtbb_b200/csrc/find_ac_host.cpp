@@ -9,6 +9,7 @@
  * open-addressing error table the kernels use (tables.cu).  First hit only.  The batch entry
  * points (btbb_b200_find_ac_dev / _host / _packed_dev / _sharded_*) never come here.
  */
+#include <stdlib.h>
 #include <string.h>
 #include "bt_math.h"
 #include "scan_hash.h"
@@ -48,8 +49,8 @@ const int CHUNK = 4096;      /* positions per packed block */
 
 }  // namespace
 
-int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,
-		      int max_ac_errors, btbb_b200_hit *hit, int *found)
+static int find_first_core(const bt_err_slot *h_err, int err_log2, const char *stream, int search_length, uint32_t lap,
+			   int max_ac_errors, btbb_b200_hit *hit, int *found)
 {
 	*found = 0;
 	if (search_length <= 0) return BTBB_B200_OK;
@@ -86,11 +87,11 @@ int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_l
 				int e = 0;
 				if (syn) {
 					e = 0xff;
-					if (ctx->h_err) {
-						const uint64_t mask = ((uint64_t)1 << ctx->err_log2) - 1;
-						uint64_t h = bt_err_hash(syn, ctx->err_log2);
+					if (h_err) {
+						const uint64_t mask = ((uint64_t)1 << err_log2) - 1;
+						uint64_t h = bt_err_hash(syn, err_log2);
 						for (;;) {
-							const bt_err_slot &sl = ctx->h_err[h];
+							const bt_err_slot &sl = h_err[h];
 							if (sl.syn == syn) { sw ^= sl.err; e = popc64(sl.err); break; }   /* Barker fixes are not counted */
 							if (sl.syn == 0) break;
 							h = (h + 1) & mask;
@@ -106,4 +107,59 @@ int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_l
 		}
 	}
 	return BTBB_B200_OK;
+}
+
+int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,
+		      int max_ac_errors, btbb_b200_hit *hit, int *found)
+{
+	return find_first_core(ctx->h_err, ctx->err_log2, stream, search_length, lap, max_ac_errors, hit, found);
+}
+
+/* The short-search host path without a context: the first hit of a btbb_find_ac call after
+ * btbb_init(table_errors), computed by the same routine compat.cu uses for searches of at most 8192
+ * positions.  The error table (what tables.cu builds and keeps a host copy of: syndrome -> pattern for
+ * up to table_errors errors in bits 0..57, bluetooth_packet.c:161-185, open addressing with
+ * bt_err_hash) is built here on first use.  For callers that only ever search short buffers and for
+ * the CPU-only tests; table_errors 0..4. */
+extern "C" int btbb_b200_find_first_smallcall(const char *stream, int search_length, uint32_t lap, int table_errors,
+					      int max_ac_errors, btbb_b200_hit *hit, int *found)
+{
+	if (!stream || !hit || !found || search_length < 0 || table_errors < 0 || table_errors > 4 || max_ac_errors < 0)
+		return btbb_b200_set_error(BTBB_B200_EINVAL, "find_first_smallcall: bad arguments");
+	static std::mutex lock;
+	static bt_err_slot *tabs[5];
+	static int logs[5];
+	{
+		std::lock_guard<std::mutex> g(lock);
+		if (table_errors > 0 && !tabs[table_errors]) {
+			uint64_t col[58];
+			for (int i = 0; i < 58; i++) col[i] = bt_syndrome_slow(1ULL << i);
+			size_t n = 0, c = 1;
+			for (int w = 1; w <= table_errors; w++) { c = c * (size_t)(58 - w + 1) / (size_t)w; n += c; }
+			int lg = 4;
+			while (((size_t)1 << lg) < 2 * n) lg++;
+			bt_err_slot *tab = (bt_err_slot *)calloc((size_t)1 << lg, sizeof(bt_err_slot));
+			if (!tab) return btbb_b200_set_error(BTBB_B200_ENOMEM, "find_first_smallcall: out of host memory");
+			const uint64_t mask = ((uint64_t)1 << lg) - 1;
+			/* every pattern of 1..table_errors bits among bits 0..57, by weight and then in index order */
+			int idx[4];
+			for (int w = 1; w <= table_errors; w++) {
+				for (int j = 0; j < w; j++) idx[j] = j;
+				for (;;) {
+					uint64_t e = 0, sy = 0;
+					for (int j = 0; j < w; j++) { e |= 1ULL << idx[j]; sy ^= col[idx[j]]; }
+					uint64_t h = bt_err_hash(sy, lg);
+					while (tab[h].syn) h = (h + 1) & mask;
+					tab[h].syn = sy; tab[h].err = e;
+					int j = w - 1;
+					while (j >= 0 && idx[j] == 58 - w + j) j--;
+					if (j < 0) break;
+					idx[j]++;
+					for (int t = j + 1; t < w; t++) idx[t] = idx[t - 1] + 1;
+				}
+			}
+			tabs[table_errors] = tab; logs[table_errors] = lg;
+		}
+	}
+	return find_first_core(tabs[table_errors], logs[table_errors], stream, search_length, lap, max_ac_errors, hit, found);
 }

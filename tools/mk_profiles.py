@@ -71,9 +71,10 @@ WORK = {"v7": "10^10 symbols, promiscuous, tables for 2 errors (BASELINE configs
         "k3": "4 x 10^9 symbols, promiscuous, tables for 3 errors", "k4": "4 x 10^9 symbols, tables for 4 errors", "k5": "2 x 10^9 symbols, tables for 5 errors",
         "decode1": "79 000 packets of the config-3 capture, 64-clock sweep, 64 full records per packet", "decode0": "79 000 packets, btbb_decode with the true clock / UAP",
         "tc16": "79 000 packets, 64-clock sweep, compact 16-bit results (the UAP sieve's input)", "sieve": "UAP sieve rounds of one call (79 000 packets, 75 piconets): the longest launch",
-        "hops": "2^27-entry hop sequence of one address", "winnow": "hop reversal: 2^21 candidates x 12 observations", "slabsort": "ordering pass of a 10^10-symbol scan (10^6 hits)"}
+        "hops": "2^27-entry hop sequence of one address", "winnow": "hop reversal: 2^21 candidates x 12 observations", "slabsort": "ordering pass of a 10^10-symbol scan (10^6 hits)",
+        "capture": "pcap records of 158 005 packets (payload 0..183 bytes) formatted on the device: the write kernel"}
 summary = []
-for name in ("v7", "known", "k3", "k4", "k5", "decode1", "decode0", "tc16", "sieve", "hops", "winnow", "slabsort"):
+for name in ("v7", "known", "k3", "k4", "k5", "decode1", "decode0", "tc16", "sieve", "hops", "winnow", "slabsort", "capture"):
     p = os.path.join(ART, f"ncu_{name}_raw.csv")
     if not (os.path.exists(p) and os.path.getsize(p) > 0):
         continue

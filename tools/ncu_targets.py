@@ -5,7 +5,7 @@
 targets: v7 (promiscuous k=2), k3 / k4 / k5 (larger error tables), known (known-LAP scan),
 decode0 (btbb_decode with the true clock), decode1 (64-clock sweep, full records), tc16 (compact
 64-clock sweep), sieve (UAP sieve: compact sweep + candidate elimination), hops (2^27-entry hop
-sequence + a winnow call)."""
+sequence + a winnow call), capture (pcap records of 158 005 packets formatted on the device)."""
 import ctypes as C
 import os
 import sys
@@ -29,6 +29,23 @@ if target == "hops":
     torch.cuda.synchronize()
     c, a = B.hop_winnow(ctx, cfg, 5, np.arange(12) * 7, np.arange(12) % 79)
     print("hops done", len(c))
+elif target == "capture":
+    n = 158005
+    rng = np.random.default_rng(5)
+    hits = np.zeros(n, dtype=B.HIT_DTYPE)
+    hits["lap"] = rng.integers(0, 1 << 24, n)
+    rec = np.zeros(n, dtype=B.DECODED_DTYPE)
+    rec["payload_length"] = rng.choice([0, 17, 20, 27, 121, 183], n)
+    rec["payload"] = rng.integers(0, 256, (n, 344), dtype=np.uint8)
+    meta = np.zeros(n, dtype=B.PCAP_META_DTYPE)
+    ctx = B.Context(0, 0)
+    dh, dr, dm = (torch.from_numpy(x.view(np.uint8).copy()).cuda() for x in (hits, rec, meta))
+    out = torch.empty(n * 440, dtype=torch.uint8, device="cuda")
+    got = C.c_int64(0)
+    for _ in range(reps):
+        B.check(lib.btbb_b200_capture_records_dev(ctx.h, 0, dh.data_ptr(), dr.data_ptr(), dm.data_ptr(), n, B.LAP_ANY, 0xFF,
+                                                  out.data_ptr(), out.numel(), C.byref(got), None))
+    print("capture bytes", got.value)
 elif target in ("v7", "k3", "k4", "k5", "known"):
     n = int(float(os.environ.get("NCU_SYMBOLS", "4e9")))
     k = {"v7": 2, "k3": 3, "k4": 4, "k5": 5, "known": 2}[target]
