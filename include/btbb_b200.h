@@ -135,6 +135,7 @@ int btbb_b200_set_offset_bias(btbb_b200_ctx *ctx, int64_t bias);
 #define BTBB_B200_OPT_PACK_THREADS        4   /* [0 = all usable CPUs, at most 32] host pack threads */
 #define BTBB_B200_OPT_TRACE               5   /* [0] timing lines of the host-buffer scan on stderr */
 #define BTBB_B200_OPT_DECODE_WIDE_STAGING 6   /* [0] 64-clock sweep: 12 warps per SM staging 32 records instead of 24 x 16 */
+#define BTBB_B200_OPT_PACK_STREAMS        7   /* [4] address streams a host pack thread advances in lock step (1, 2, 4 or 8) */
 int btbb_b200_set_option(btbb_b200_ctx *ctx, int option, int64_t value);
 
 /* Measurement hook (bench.py's roofline): with profiling on, every scan records CUDA events right

@@ -194,7 +194,7 @@ def pcap_bredr(hits, dec, meta, reflap=LAP_ANY, refuap=0xFF):
     return buf.tobytes()
 
 
-OPT_TILE_KERNEL_ONLY, OPT_HOST_BYTE_ROUTE, OPT_HOST_SPLIT_PERMILLE, OPT_PACK_THREADS, OPT_TRACE, OPT_DECODE_WIDE_STAGING = 1, 2, 3, 4, 5, 6
+OPT_TILE_KERNEL_ONLY, OPT_HOST_BYTE_ROUTE, OPT_HOST_SPLIT_PERMILLE, OPT_PACK_THREADS, OPT_TRACE, OPT_DECODE_WIDE_STAGING, OPT_PACK_STREAMS = 1, 2, 3, 4, 5, 6, 7
 MODE_DECODE, MODE_TRY_CLOCKS, MODE_PAYLOAD, MODE_CRC_CHECK, MODE_RAW, MODE_FLAG_RAW_PAYLOAD = 0, 1, 2, 3, 16, 0x100
 
 

@@ -115,7 +115,7 @@ struct btbb_b200_ctx {
 	void *d_scratch[4];          /* grow-only device scratch of the host-buffer entry points */
 	size_t scratch_cap[4];
 	cudaEvent_t ev_reset;        /* host-buffer scan: the counter reset has been enqueued */
-	int opt_tile_only, opt_host_bytes, opt_host_split, opt_pack_threads, opt_trace, opt_decode_wide;   /* btbb_b200_set_option */
+	int opt_tile_only, opt_host_bytes, opt_host_split, opt_pack_threads, opt_trace, opt_decode_wide, opt_pack_streams;   /* btbb_b200_set_option */
 	cudaEvent_t prof_ev[2];      /* btbb_b200_set_profiling: around the bulk scan kernel */
 	int prof_on, prof_valid;
 	cudaEvent_t ev_done;         /* active lane: the pending scan's last enqueued operation */
@@ -165,6 +165,7 @@ int bt_try_clocks_compact(btbb_b200_ctx *ctx, const uint8_t *d_stream, int64_t s
 
 /* host_pack.cpp */
 extern "C" void bt_pack_range(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out);
+extern "C" void bt_pack_range_streams(const char *stream, int64_t first, int64_t nwords, int64_t limit, uint32_t *out, int streams);
 
 /* find_ac_host.cpp, decode_host.cpp: the small-call path of the classic single-packet surface */
 int bt_find_first_cpu(const btbb_b200_ctx *ctx, const char *stream, int search_length, uint32_t lap,

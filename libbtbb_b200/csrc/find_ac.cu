@@ -1108,6 +1108,7 @@ extern "C" int btbb_b200_set_option(btbb_b200_ctx *ctx, int option, int64_t valu
 	case BTBB_B200_OPT_PACK_THREADS: ctx->opt_pack_threads = (int)(value < 0 ? 0 : value > 128 ? 128 : value); break;
 	case BTBB_B200_OPT_TRACE: ctx->opt_trace = value != 0; break;
 	case BTBB_B200_OPT_DECODE_WIDE_STAGING: ctx->opt_decode_wide = value != 0; break;
+	case BTBB_B200_OPT_PACK_STREAMS: ctx->opt_pack_streams = (int)(value < 1 ? 1 : value > 8 ? 8 : value); break;
 	default: return btbb_b200_set_error(BTBB_B200_EINVAL, "set_option: unknown option");
 	}
 	return BTBB_B200_OK;

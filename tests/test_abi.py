@@ -69,6 +69,19 @@ def test_host_pack_bit_order_and_limit(product_lib):
             pad = (-(n - first)) % 32
             want = np.packbits(np.concatenate([s[first:], np.zeros(pad, dtype=np.uint8)]), bitorder="little").view("<u4")
             assert (out == want).all(), (n, first)
+    # the multi-stream form (several address ranges of a block advanced in lock step): same words
+    g = product_lib.bt_pack_range_streams
+    g.argtypes = f.argtypes + [C.c_int]
+    g.restype = None
+    for n in (4096 * 32, 4096 * 32 + 31, 16384 * 32, 16384 * 32 + 777, 5000 * 32 + 5):
+        s = rng.integers(0, 2, n, dtype=np.uint8)
+        guard = np.concatenate([s, np.full(64, 0xFF, dtype=np.uint8)])
+        nwords = (n + 31) // 32
+        want = np.packbits(np.concatenate([s, np.zeros((-n) % 32, dtype=np.uint8)]), bitorder="little").view("<u4")
+        for streams in (1, 2, 3, 4, 8, 16):
+            out = np.zeros(nwords, dtype=np.uint32)
+            g(guard.ctypes.data, 0, nwords, n, out.ctypes.data, streams)
+            assert (out == want).all(), (n, streams)
 
 
 C_CALLER = r"""
