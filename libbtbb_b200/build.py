@@ -1,6 +1,8 @@
 """Build libbtbb.so.1 (B200) in-tree with nvcc for sm_100a.
 
     python -m libbtbb_b200.build [--force] [--ptxas-verbose]
+    python -m libbtbb_b200.build --compose-reference <upstream checkout>     # lib/full/libbtbb.so.1
+    python -m libbtbb_b200.build --install <prefix> [--full]                 # upstream's install layout
 
 The shared object lands in libbtbb_b200/lib/libbtbb.so.1 (SONAME libbtbb.so.1, the
 name upstream installs, lib/src/CMakeLists.txt:43-52) so it travels with the source
@@ -100,6 +102,37 @@ def _dev_files():
             f.write(pc)
 
 
+def install(prefix, full=False):
+    """Upstream's install layout under `prefix` (lib/src/CMakeLists.txt:43-68, lib/libbtbb.pc.in): include/btbb.h
+    (+ btbb_b200.h), lib/libbtbb.so.1, the libbtbb.so link, libbtbb.a, lib/pkgconfig/libbtbb.pc -- what
+    pkg-config and upstream's cmake/modules/FindBTBB.cmake (LIBBTBB_DIR=<prefix>) look for.  full=True installs
+    the composed library (every symbol of upstream's btbb.h) instead of the packet layer alone."""
+    import shutil
+    build()
+    src_lib = FULL_LIB if full else LIB
+    if not os.path.exists(src_lib):
+        raise RuntimeError(src_lib + " has not been built")
+    inc, lib = os.path.join(prefix, "include"), os.path.join(prefix, "lib")
+    os.makedirs(inc, exist_ok=True)
+    os.makedirs(os.path.join(lib, "pkgconfig"), exist_ok=True)
+    for h in ("btbb.h", "btbb_b200.h"):
+        shutil.copy(os.path.join(HERE, "..", "include", h), inc)
+    shutil.copy(src_lib, os.path.join(lib, "libbtbb.so.1"))
+    link = os.path.join(lib, "libbtbb.so")
+    if os.path.lexists(link):
+        os.remove(link)
+    os.symlink("libbtbb.so.1", link)
+    if os.path.exists(STATIC) and not full:
+        shutil.copy(STATIC, lib)
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")
+    with open(os.path.join(lib, "pkgconfig", "libbtbb.pc"), "w") as f:
+        f.write("prefix=%s\nexec_prefix=${prefix}\nlibdir=${prefix}/lib\nincludedir=${prefix}/include\n\n"
+                "Name: Bluetooth Baseband Library\nDescription: C Utility Library (B200 build of the packet layer)\n"
+                "Version: 0.1-b200\nCflags: -I${includedir}/\nLibs: -L${libdir} -lbtbb\n"
+                "Libs.private: -L%s -lcudart -lstdc++ -lm -ldl -lpthread\n" % (os.path.abspath(prefix), cuda_lib))
+    return prefix
+
+
 FULL_LIB = os.path.join(LIBDIR, "full", "libbtbb.so.1")
 REF_UNITS = ["bluetooth_piconet.c", "bluetooth_le_packet.c", "companies.c", "pcap.c", "pcapng.c", "pcapng-bt.c"]
 
@@ -138,6 +171,9 @@ if __name__ == "__main__":
         i = sys.argv.index("--compose-reference")
         root = sys.argv[i + 1] if i + 1 < len(sys.argv) and not sys.argv[i + 1].startswith("-") else "/root/reference"
         print(compose(root, verbose="-v" in sys.argv))
+        sys.exit(0)
+    if "--install" in sys.argv:
+        print(install(sys.argv[sys.argv.index("--install") + 1], full="--full" in sys.argv))
         sys.exit(0)
     build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_verbose="--ptxas-verbose" in sys.argv)
     print(LIB)

@@ -170,3 +170,37 @@ def test_pkg_config_and_static_library(product_lib, tmp_path):
     assert int(out[0]) == want_rc and out[3] == "4e7a2cce331a3ae2"
     ldd = subprocess.run(["ldd", str(sta)], capture_output=True, text=True).stdout
     assert "libbtbb" not in ldd
+
+
+def test_install_layout_is_found_by_upstreams_cmake_module(product_lib, tmp_path):
+    """`python -m libbtbb_b200.build --install <prefix>` lays the library out the way upstream's install step
+    does; a CMake project that uses upstream's own FindBTBB.cmake (cmake/modules/FindBTBB.cmake:24-36, read
+    from the reference checkout where there is one) finds it through LIBBTBB_DIR, builds and runs."""
+    import shutil
+    import subprocess
+    import torch
+    from libbtbb_b200 import build
+    module_dir = "/root/reference/cmake/modules"
+    if not shutil.which("cmake") or not os.path.exists(os.path.join(module_dir, "FindBTBB.cmake")):
+        pytest.skip("needs cmake and an upstream checkout")
+    prefix = tmp_path / "prefix"
+    build.install(str(prefix))
+    assert sorted(os.listdir(prefix / "include")) == ["btbb.h", "btbb_b200.h"]
+    assert os.readlink(prefix / "lib" / "libbtbb.so") == "libbtbb.so.1" and (prefix / "lib" / "pkgconfig" / "libbtbb.pc").exists()
+    proj = tmp_path / "proj"
+    proj.mkdir()
+    (proj / "caller.c").write_text(C_CALLER)
+    (proj / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.5)\nproject(caller C)\n"
+        f"list(APPEND CMAKE_MODULE_PATH {module_dir})\n"
+        "find_package(BTBB REQUIRED)\n"
+        "include_directories(${LIBBTBB_INCLUDE_DIR})\n"
+        "add_executable(caller caller.c)\n"
+        "target_link_libraries(caller ${LIBBTBB_LIBRARIES})\n")
+    env = dict(os.environ, LIBBTBB_DIR=str(prefix), PKG_CONFIG_PATH="")
+    bdir = tmp_path / "b"
+    subprocess.run(["cmake", "-S", str(proj), "-B", str(bdir)], env=env, check=True, capture_output=True)
+    subprocess.run(["cmake", "--build", str(bdir)], env=env, check=True, capture_output=True)
+    out = subprocess.run([str(bdir / "caller")], capture_output=True, text=True, check=True,
+                         env=dict(os.environ, LD_LIBRARY_PATH=str(prefix / "lib"))).stdout.split()
+    assert int(out[0]) == (0 if torch.cuda.is_available() else -2) and out[3] == "4e7a2cce331a3ae2"
