@@ -87,11 +87,14 @@ def main(path):
     os.dup2(devnull, 1)
     try:
         # ---- survey mode (bluetooth_piconet.c:851-858) ----
+        import time
         L.btbb_init_survey()
+        t0 = time.perf_counter()
         for i in order:
             p = make_packet(i)
             L.btbb_process_packet(p, None)
             L.btbb_packet_unref(p)
+        out["survey_us_per_packet"] = 1e6 * (time.perf_counter() - t0) / max(len(order), 1)
         survey = []
         while True:
             pn = L.btbb_next_survey_result()
