@@ -8,4 +8,5 @@ for tool in memcheck racecheck; do
   grep -E "ERROR SUMMARY|passed|failed" $O/$tool.log | tail -3 >> $O/summary.txt
 done
 cat $O/summary.txt
-KBENCH_MODES=v1,v4g python tools/kbench.py --symbols 4000000000 --iters 5 --lap 0x9e8b33 --check 2>&1 | tail -1
+# this round's new kernels (decode rewrite with forced types, device capture formatter, winnow): tools/gpu_job_final2.sh
+python tools/kbench.py --symbols 4000000000 --iters 5 --lap 0x9e8b33 --check 2>&1 | tail -1
